@@ -1,0 +1,118 @@
+"""The CPU port (oracle/reference_port.py) against outputs of the unmodified reference
+(tests/golden/, minted by oracle/make_golden.py).  fp32 vs fp32, so the bound is accumulation noise."""
+import pytest
+import torch
+
+from oracle import reference_port as rp
+from oracle.cases import CASES_DIT, CASES_DENOISE, CASES_VAE, ROLLOUT, seeded_rand, seeded_randn, subsample_image
+from oracle.weights import DiTConfig, VAEConfig, dummy_prompt, make_dit_state, make_vae_state, w_key_actions
+
+torch.set_num_threads(8)
+_state = {}
+
+
+def dit_state(depth, degenerate=False):
+    key = ("dit", depth, degenerate)
+    if key not in _state:
+        _state[key] = make_dit_state(DiTConfig(depth=depth), seed=0, degenerate=degenerate)
+    return _state[key]
+
+
+def vae_state(enc, dec):
+    key = ("vae", enc, dec)
+    if key not in _state:
+        _state[key] = make_vae_state(VAEConfig(enc_depth=enc, dec_depth=dec), seed=0)
+    return _state[key]
+
+
+def test_schedule_known_answers(golden):
+    g = golden("schedule")
+    betas = rp.sigmoid_beta_schedule(1000)
+    assert betas.dtype == torch.float64
+    assert torch.equal(betas, g["betas_f64"])
+    abar = rp.alphas_cumprod_table()
+    assert torch.equal(abar, g["alphas_cumprod_f32"])
+    # KATs recorded in SURVEY.md §8(a3)
+    assert abs(float(betas[0]) - 3.0024917e-4) < 1e-10
+    assert abs(float(abar[15]) - 0.99499559) < 1e-7
+    assert abs(float(abar[999]) - 1.0000775e-4) < 1e-9
+
+
+def test_noise_levels_truncate():
+    assert rp.noise_levels(100)[:4] == [0, 9, 19, 29] and rp.noise_levels(100)[-1] == 999
+    assert rp.noise_levels(10) == [0, 99, 199, 299, 399, 499, 599, 699, 799, 899, 999]
+
+
+@pytest.mark.parametrize("name", list(CASES_DIT))
+def test_dit_forward_matches_reference(golden, name):
+    c = CASES_DIT[name]
+    cfg = DiTConfig(depth=c["depth"])
+    x = seeded_randn((c["B"], c["T"], 16, 18, 32), c["seed"])
+    g = golden("dit_forward")
+    assert float(x.double().sum()) == float(g[f"{name}.x_sum"])      # RNG stream unchanged
+    t = torch.tensor(c["t"]).reshape(c["B"], c["T"])
+    a = w_key_actions(c["B"], c["T"]) if c["actions"] else None
+    v = rp.dit_forward(dit_state(c["depth"], c["degenerate"]), cfg, x, t, a)
+    ref = g[f"{name}.v"]
+    assert v.shape == ref.shape
+    assert float((v - ref).abs().max()) < 2e-4, float((v - ref).abs().max())
+
+
+@pytest.mark.parametrize("name", list(CASES_DENOISE))
+def test_denoise_step_matches_reference(golden, name):
+    c = CASES_DENOISE[name]
+    cfg = DiTConfig(depth=c["depth"])
+    x = seeded_randn((c["B"], c["frames"], 16, 18, 32), c["seed"])
+    a = w_key_actions(c["B"], c["frames"]) if c["actions"] else None
+    xp, v = rp.denoise_step(dit_state(c["depth"]), cfg, x, a, c["noise_idx"], 15,
+                            rp.noise_levels(c["noise_steps"]), rp.alphas_cumprod_table(), c["start_frame"])
+    g = golden("denoise_step")
+    assert float((v - g[f"{name}.v_pred"]).abs().max()) < 2e-4
+    # x_pred divides by sqrt(1/abar - 1): tiny at t=15 for context frames, so compare relatively
+    ref = g[f"{name}.x_pred"]
+    assert float(((xp - ref).abs() / (1 + ref.abs())).max()) < 2e-3
+    assert float((xp[:, -1] - ref[:, -1]).abs().max()) < 5e-4
+
+
+@pytest.mark.parametrize("name", list(CASES_VAE))
+def test_vae_matches_reference(golden, name):
+    c = CASES_VAE[name]
+    cfg = VAEConfig(enc_depth=c["enc_depth"], dec_depth=c["dec_depth"])
+    sd = vae_state(c["enc_depth"], c["dec_depth"])
+    g = golden("vae")
+    img = seeded_rand((c["N"], 3, 360, 640), c["seed"]) * 2 - 1
+    mean = rp.vae_encode_mean(sd, cfg, img)
+    assert float((mean - g[f"{name}.mean"]).abs().max()) < 5e-4
+    dec = rp.vae_decode(sd, cfg, seeded_randn((c["N"], 576, 16), c["seed"] + 1))
+    assert float((subsample_image(dec) - g[f"{name}.dec_sub"]).abs().max()) < 5e-4
+    assert abs(float(dec.double().sum()) - float(g[f"{name}.dec_sum"])) < 1e-3 * float(g[f"{name}.dec_abs_sum"])
+
+
+def test_rollout_matches_reference(golden):
+    c = ROLLOUT
+    dcfg = DiTConfig(depth=c["depth"])
+    vcfg = VAEConfig(enc_depth=c["enc_depth"], dec_depth=c["dec_depth"])
+    g = golden("rollout")
+    vsd = vae_state(c["enc_depth"], c["dec_depth"])
+    lat = rp.encode_prompt(vsd, vcfg, dummy_prompt(5)[None, : c["n_prompt"]])
+    assert float((lat - g["prompt_latents"]).abs().max()) < 5e-4
+    gen = torch.Generator().manual_seed(c["seed"])
+    x = rp.rollout(dit_state(c["depth"]), dcfg, g["prompt_latents"], w_key_actions(1, c["total_frames"]),
+                   c["total_frames"], c["noise_steps"], lambda i: torch.randn((1, 1, 16, 18, 32), generator=gen))
+    assert float((x - g["latents"]).abs().max()) < 2e-3
+    u8 = rp.decode_to_uint8(vsd, vcfg, g["latents"])
+    diff = (u8[:, :, ::8, ::8].int() - g["frames_u8_sub"].int()).abs()
+    assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 0.01   # truncation flips only
+
+
+def test_bf16_rounding_model_is_close_to_fp32():
+    """The autocast-rounding emulation stays within the calibrated bf16-vs-fp32 gap."""
+    c = CASES_DIT["d2_b1_t5_act"]
+    cfg = DiTConfig(depth=2)
+    x = seeded_randn((1, 5, 16, 18, 32), c["seed"])
+    t = torch.tensor(c["t"]).reshape(1, 5)
+    a = w_key_actions(1, 5)
+    v32 = rp.dit_forward(dit_state(2), cfg, x, t, a, rp.FP32)
+    v16 = rp.dit_forward(dit_state(2), cfg, x, t, a, rp.BF16)
+    err = (v32 - v16).abs()
+    assert 0 < float(err.max()) < 6e-2 and float(err.mean()) < 1.2e-2
