@@ -1,0 +1,92 @@
+// Causal attention over the (<= 8) frames of the sliding window, one problem per (rollout, spatial
+// position, head), with the 1-D rotary embedding on the frame index fused.
+//
+// Replaces TemporalAxialAttention's rearrange + rotate_queries_or_keys + causal SDPA (reference
+// model/attention.py:52-66; rotary_embedding_torch.py:186-209: positions are window-relative
+// arange(T), theta 1e4).  T x T scores with T <= 5 are far too small for tensor cores: this kernel
+// is L2/HBM-bound (reads the 3*D-wide qkv rows once, writes D), one warp per problem, each lane owns
+// one rotary pair (2 of the 64 head dims), dot products reduced with shuffles.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gtav {
+
+static constexpr int TA_WARPS = 8;
+
+template <int T>
+__global__ void __launch_bounds__(TA_WARPS * 32)
+attn_temporal_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int B, int P, int heads,
+                     const float2* __restrict__ rot) {
+    const int lane = threadIdx.x & 31;
+    const long wg = static_cast<long>(blockIdx.x) * TA_WARPS + (threadIdx.x >> 5);
+    if (wg >= static_cast<long>(B) * P * heads) return;
+    const int head = static_cast<int>(wg % heads);
+    const int pos = static_cast<int>((wg / heads) % P);
+    const int b = static_cast<int>(wg / (static_cast<long>(heads) * P));
+    const int D = heads * 64;
+    const int ld = 3 * D;
+
+    float2 q[T], k[T], v[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const size_t row = (static_cast<size_t>(b) * T + t) * P + pos;
+        const bf16* base = qkv + row * ld + head * 64 + 2 * lane;
+        const uint32_t qu = *reinterpret_cast<const uint32_t*>(base);
+        const uint32_t ku = *reinterpret_cast<const uint32_t*>(base + D);
+        const uint32_t vu = *reinterpret_cast<const uint32_t*>(base + 2 * D);
+        const float2 cs = rot[t * 32 + lane];
+        const float2 qx = unpack_bf16x2(qu), kx = unpack_bf16x2(ku);
+        // rotate in fp32, round once to bf16 (apply_rotary_emb casts back to the input dtype)
+        q[t] = make_float2(bf16_round(qx.x * cs.x - qx.y * cs.y), bf16_round(qx.y * cs.x + qx.x * cs.y));
+        k[t] = make_float2(bf16_round(kx.x * cs.x - kx.y * cs.y), bf16_round(kx.y * cs.x + kx.x * cs.y));
+        v[t] = unpack_bf16x2(vu);
+    }
+#pragma unroll
+    for (int i = 0; i < T; ++i) {
+        float s[T];
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            s[j] = warp_sum(q[i].x * k[j].x + q[i].y * k[j].y) * 0.125f;
+            m = fmaxf(m, s[j]);
+        }
+        float l = 0.f;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            s[j] = __expf(s[j] - m);
+            l += s[j];
+        }
+        const float inv = 1.0f / l;
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            const float p = bf16_round(s[j] * inv);          // probabilities enter P@V as bf16
+            acc.x += p * v[j].x;
+            acc.y += p * v[j].y;
+        }
+        const size_t row = (static_cast<size_t>(b) * T + i) * P + pos;
+        *reinterpret_cast<uint32_t*>(out + row * D + head * 64 + 2 * lane) = pack_bf16x2(acc.x, acc.y);
+    }
+}
+
+int launch_attention_temporal(const bf16* qkv, bf16* out, int B, int T, int positions, int heads, const float2* rot,
+                              cudaStream_t s) {
+    const long problems = static_cast<long>(B) * positions * heads;
+    if (problems <= 0) return 0;
+    const int grid = static_cast<int>((problems + TA_WARPS - 1) / TA_WARPS);
+#define GTAV_TA(TT)                                                                                       \
+    case TT:                                                                                              \
+        attn_temporal_kernel<TT><<<grid, TA_WARPS * 32, 0, s>>>(qkv, out, B, positions, heads, rot);       \
+        break;
+    switch (T) {
+        GTAV_TA(1) GTAV_TA(2) GTAV_TA(3) GTAV_TA(4) GTAV_TA(5) GTAV_TA(6) GTAV_TA(7) GTAV_TA(8)
+        default:
+            set_error("temporal attention: window of %d frames unsupported (1..8)", T);
+            return -1;
+    }
+#undef GTAV_TA
+    GTAV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace gtav

@@ -1,0 +1,268 @@
+// Host-side DiT engine: owns the per-(B,T) launch plan (TMA descriptors, workspace carve-up) and
+// enqueues the kernel sequence that stands in for DiT.forward (reference model/dit.py:343-376) and
+// SpatioTemporalDiTBlock.forward (model/dit.py:200-225).  No allocation, no host sync: everything is
+// launched on the caller's stream so a whole step can be captured into a CUDA graph.
+#include <new>
+#include <vector>
+
+#include "../../include/gtav_b200.h"
+#include "kernels.h"
+
+using namespace gtav;
+
+struct gtav_dit_s {
+    gtav_dit_config cfg;
+    gtav_dit_weights w;
+    std::vector<gtav_dit_half> halves;
+    int tokens;       // grid_h * grid_w
+    int mod_width;    // depth*2*6D + 2D
+    int patch_k;      // C*p*p
+    int out_feat;     // p*p*C
+};
+
+struct gtav_dit_plan_s {
+    gtav_dit_t eng;
+    int B, T, M, R;
+    // workspace slices
+    bf16 *xa, *h, *hn, *qkv, *att, *mlp, *yfin, *temb, *aemb, *h1, *cact, *mod;
+    GemmOp g_t0, g_t2, g_ada, g_patch, g_final;
+    std::vector<GemmOp> g_qkv, g_out, g_fc1, g_fc2;
+};
+
+namespace {
+
+struct Carver {
+    uint8_t* base;
+    size_t off = 0;
+    explicit Carver(void* p) : base(static_cast<uint8_t*>(p)) {}
+    bf16* take(size_t elems) {
+        bf16* r = reinterpret_cast<bf16*>(base + off);
+        off += (elems * sizeof(bf16) + 1023) & ~size_t(1023);
+        return r;
+    }
+};
+
+void carve(gtav_dit_plan_s* p, void* ws, size_t* total) {
+    const gtav_dit_s* e = p->eng;
+    const size_t M = p->M, R = p->R, D = e->cfg.hidden;
+    Carver c(ws);
+    p->xa = c.take(M * 64);
+    p->h = c.take(M * D);
+    p->hn = c.take(M * D);
+    p->qkv = c.take(M * 3 * D);
+    p->att = c.take(M * D);
+    p->mlp = c.take(M * 4 * D);
+    p->yfin = c.take(M * 64);
+    p->temb = c.take(R * 256);
+    p->aemb = c.take(R * D);
+    p->h1 = c.take(R * D);
+    p->cact = c.take(R * D);
+    p->mod = c.take(R * static_cast<size_t>(e->mod_width));
+    *total = c.off;
+}
+
+GemmParams gp(bf16* out, int ldo, const void* bias, int M, int N, int K) {
+    GemmParams p{};
+    p.out = out; p.ldo = ldo; p.bias = static_cast<const bf16*>(bias);
+    p.M = M; p.N = N; p.K = K; p.rows_per_frame = 1;
+    return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gtav_last_error(void) { return get_error(); }
+int gtav_abi_version(void) { return 1; }
+
+int gtav_dit_create(const gtav_dit_config* cfg, const gtav_dit_weights* w, gtav_dit_t* out) {
+    if (!cfg || !w || !out) { set_error("dit_create: null argument"); return -1; }
+    if (cfg->hidden != 1024 || cfg->heads != 16 || cfg->grid_h * cfg->grid_w != 144 ||
+        cfg->in_channels * cfg->patch * cfg->patch != 64 || cfg->depth < 1 || cfg->max_frames < 1 || cfg->max_frames > 8) {
+        set_error("dit_create: unsupported geometry (hidden=%d heads=%d grid=%dx%d patch=%d C=%d depth=%d max_frames=%d); "
+                  "kernels are built for hidden 1024, 16 heads of 64, 144 tokens, 64 patch features",
+                  cfg->hidden, cfg->heads, cfg->grid_h, cfg->grid_w, cfg->patch, cfg->in_channels, cfg->depth, cfg->max_frames);
+        return -1;
+    }
+    if (cfg->act_dim < 0 || cfg->act_dim > 64 || (cfg->act_dim > 0 && (!w->act_w || !w->act_b))) {
+        set_error("dit_create: bad external_cond configuration (act_dim=%d)", cfg->act_dim);
+        return -1;
+    }
+    gtav_dit_s* e = new (std::nothrow) gtav_dit_s();
+    if (!e) { set_error("dit_create: out of host memory"); return -4; }
+    e->cfg = *cfg;
+    e->w = *w;
+    e->halves.assign(w->halves, w->halves + 2 * cfg->depth);
+    e->w.halves = e->halves.data();
+    e->tokens = cfg->grid_h * cfg->grid_w;
+    e->mod_width = cfg->depth * 2 * 6 * cfg->hidden + 2 * cfg->hidden;
+    e->patch_k = cfg->in_channels * cfg->patch * cfg->patch;
+    e->out_feat = e->patch_k;
+    *out = e;
+    return 0;
+}
+
+void gtav_dit_destroy(gtav_dit_t h) { delete h; }
+int gtav_dit_mod_width(gtav_dit_t h) { return h ? h->mod_width : 0; }
+
+size_t gtav_dit_workspace_bytes(gtav_dit_t h, int B, int T, int cond_rows) {
+    if (!h || B <= 0 || T <= 0 || cond_rows <= 0) return 0;
+    gtav_dit_plan_s tmp{};
+    tmp.eng = h; tmp.B = B; tmp.T = T; tmp.M = B * T * h->tokens; tmp.R = cond_rows;
+    size_t total = 0;
+    carve(&tmp, nullptr, &total);
+    return total;
+}
+
+int gtav_dit_plan_create(gtav_dit_t h, int B, int T, int cond_rows, void* workspace, size_t workspace_bytes,
+                         gtav_dit_plan_t* out) {
+    if (!h || !workspace || !out) { set_error("dit_plan_create: null argument"); return -1; }
+    if (B <= 0 || T <= 0 || T > h->cfg.max_frames || cond_rows <= 0) {
+        set_error("dit_plan_create: B=%d T=%d cond_rows=%d out of range (T <= max_frames=%d)", B, T, cond_rows, h->cfg.max_frames);
+        return -1;
+    }
+    if (reinterpret_cast<uintptr_t>(workspace) & 1023) { set_error("dit_plan_create: workspace must be 1024-byte aligned"); return -1; }
+    gtav_dit_plan_s* p = new (std::nothrow) gtav_dit_plan_s();
+    if (!p) { set_error("dit_plan_create: out of host memory"); return -4; }
+    p->eng = h; p->B = B; p->T = T; p->M = B * T * h->tokens; p->R = cond_rows;
+    size_t need = 0;
+    carve(p, workspace, &need);
+    if (need > workspace_bytes) {
+        set_error("dit_plan_create: workspace too small (%zu < %zu)", workspace_bytes, need);
+        delete p;
+        return -1;
+    }
+    const int D = h->cfg.hidden, M = p->M, R = p->R, S = h->tokens, W = h->mod_width;
+    const gtav_dit_weights& w = h->w;
+    int rc = 0;
+    // conditioning chain (rows = R)
+    rc |= gemm_prepare(&p->g_t0, p->temb, 256, static_cast<const bf16*>(w.t0_w), 256, gp(p->h1, D, w.t0_b, R, D, 256), EPI_BIAS_SILU);
+    {
+        GemmParams q = gp(p->cact, D, w.t2_b, R, D, D);
+        if (h->cfg.act_dim > 0) { q.res = p->aemb; q.ldr = D; }
+        rc |= gemm_prepare(&p->g_t2, p->h1, D, static_cast<const bf16*>(w.t2_w), D, q, EPI_BIAS_RES_SILU);
+    }
+    rc |= gemm_prepare(&p->g_ada, p->cact, D, static_cast<const bf16*>(w.ada_w), D, gp(p->mod, W, w.ada_b, R, W, D), EPI_BIAS);
+    // backbone
+    rc |= gemm_prepare(&p->g_patch, p->xa, 64, static_cast<const bf16*>(w.patch_w), 64, gp(p->h, D, w.patch_b, M, D, 64), EPI_BIAS);
+    const int nh = 2 * h->cfg.depth;
+    p->g_qkv.resize(nh); p->g_out.resize(nh); p->g_fc1.resize(nh); p->g_fc2.resize(nh);
+    for (int i = 0; i < nh && rc == 0; ++i) {
+        const gtav_dit_half& hw = h->halves[i];
+        const bf16* modl = p->mod + static_cast<size_t>(i) * 6 * D;
+        rc |= gemm_prepare(&p->g_qkv[i], p->hn, D, static_cast<const bf16*>(hw.qkv_w), D, gp(p->qkv, 3 * D, nullptr, M, 3 * D, D), EPI_STORE);
+        GemmParams q = gp(p->h, D, hw.out_b, M, D, D);
+        q.res = p->h; q.ldr = D; q.gate = modl + 2 * D; q.gate_ld = W; q.rows_per_frame = S;
+        rc |= gemm_prepare(&p->g_out[i], p->att, D, static_cast<const bf16*>(hw.out_w), D, q, EPI_BIAS_GATE_RES);
+        rc |= gemm_prepare(&p->g_fc1[i], p->hn, D, static_cast<const bf16*>(hw.fc1_w), D, gp(p->mlp, 4 * D, hw.fc1_b, M, 4 * D, D), EPI_BIAS_GELU_TANH);
+        GemmParams r = gp(p->h, D, hw.fc2_b, M, D, 4 * D);
+        r.res = p->h; r.ldr = D; r.gate = modl + 5 * D; r.gate_ld = W; r.rows_per_frame = S;
+        rc |= gemm_prepare(&p->g_fc2[i], p->mlp, 4 * D, static_cast<const bf16*>(hw.fc2_w), 4 * D, r, EPI_BIAS_GATE_RES);
+    }
+    rc |= gemm_prepare(&p->g_final, p->hn, D, static_cast<const bf16*>(w.final_w), D, gp(p->yfin, 64, w.final_b, M, h->out_feat, D), EPI_BIAS);
+    if (rc) { delete p; return rc < 0 ? rc : -1; }
+    *out = p;
+    return 0;
+}
+
+void gtav_dit_plan_destroy(gtav_dit_plan_t p) { delete p; }
+
+int gtav_dit_conditioning(gtav_dit_plan_t p, const int64_t* t, const float* actions, gtav_stream_t stream) {
+    if (!p || !t) { set_error("dit_conditioning: null argument"); return -1; }
+    const gtav_dit_s* e = p->eng;
+    const bool use_act = e->cfg.act_dim > 0 && actions != nullptr;
+    int rc = launch_cond_prep(t, use_act ? actions : nullptr, e->cfg.act_dim, p->R, e->w.temb_freqs,
+                              static_cast<const bf16*>(e->w.act_w), static_cast<const bf16*>(e->w.act_b), p->temb,
+                              p->aemb, e->cfg.hidden, stream);
+    if (rc) return rc;
+    if ((rc = gemm_run(&p->g_t0, stream))) return rc;
+    // `c += external_cond(a)` only when an action tensor is passed (dit.py:363): toggle the residual
+    GemmOp t2 = p->g_t2;
+    if (!use_act) t2.p.res = nullptr;
+    if ((rc = gemm_run(&t2, stream))) return rc;
+    return gemm_run(&p->g_ada, stream);
+}
+
+int gtav_dit_backbone(gtav_dit_plan_t p, const void* x, int x_is_bf16, const int* frame_row, void* out,
+                      gtav_stream_t stream) {
+    if (!p || !x || !out) { set_error("dit_backbone: null argument"); return -1; }
+    const gtav_dit_s* e = p->eng;
+    const gtav_dit_config& c = e->cfg;
+    const int D = c.hidden, M = p->M, S = e->tokens, W = e->mod_width, F = p->B * p->T;
+    int rc = launch_patchify(x, x_is_bf16, p->xa, 64, F, c.in_channels, c.grid_h * c.patch, c.grid_w * c.patch, c.patch, 1.f, stream);
+    if (rc) return rc;
+    if ((rc = gemm_run(&p->g_patch, stream))) return rc;
+    const float2* rot_s = reinterpret_cast<const float2*>(e->w.rot_spatial);
+    const float2* rot_t = reinterpret_cast<const float2*>(e->w.rot_temporal);
+    for (int i = 0; i < 2 * c.depth; ++i) {
+        const int off = i * 6 * D;          // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
+        GemmOp g_out = p->g_out[i], g_fc2 = p->g_fc2[i];
+        g_out.p.frame_row = frame_row;
+        g_fc2.p.frame_row = frame_row;
+        if ((rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, off, off + D, frame_row, S, stream))) return rc;
+        if ((rc = gemm_run(&p->g_qkv[i], stream))) return rc;
+        if ((i & 1) == 0) rc = launch_attention_seq(p->qkv, p->att, F, S, c.heads, rot_s, 32, stream);
+        else rc = launch_attention_temporal(p->qkv, p->att, p->B, p->T, S, c.heads, rot_t, stream);
+        if (rc) return rc;
+        if ((rc = gemm_run(&g_out, stream))) return rc;
+        if ((rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, off + 3 * D, off + 4 * D, frame_row, S, stream))) return rc;
+        if ((rc = gemm_run(&p->g_fc1[i], stream))) return rc;
+        if ((rc = gemm_run(&g_fc2, stream))) return rc;
+    }
+    const int foff = 2 * c.depth * 6 * D;   // final layer: shift, scale
+    if ((rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, foff, foff + D, frame_row, S, stream))) return rc;
+    if ((rc = gemm_run(&p->g_final, stream))) return rc;
+    return launch_dit_unpatchify(p->yfin, static_cast<bf16*>(out), F, c.in_channels, c.grid_h, c.grid_w, c.patch, stream);
+}
+
+int gtav_dit_forward(gtav_dit_plan_t p, const void* x, int x_is_bf16, const int64_t* t, const float* actions,
+                     void* out, gtav_stream_t stream) {
+    if (!p) { set_error("dit_forward: null plan"); return -1; }
+    if (p->R != p->B * p->T) {
+        set_error("dit_forward: plan was created with cond_rows=%d, need B*T=%d", p->R, p->B * p->T);
+        return -1;
+    }
+    int rc = gtav_dit_conditioning(p, t, actions, stream);
+    if (rc) return rc;
+    return gtav_dit_backbone(p, x, x_is_bf16, nullptr, out, stream);
+}
+
+// ---------------------------------------------------------------------------- stand-alone kernels
+int gtav_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
+                   int epilogue, const void* bias, const void* res, int ldr, const void* gate, int gate_ld,
+                   const int* frame_row, int rows_per_frame, int bn, gtav_stream_t stream) {
+    GemmParams p{};
+    p.out = static_cast<bf16*>(out); p.ldo = ldo; p.bias = static_cast<const bf16*>(bias);
+    p.res = static_cast<const bf16*>(res); p.ldr = ldr; p.gate = static_cast<const bf16*>(gate); p.gate_ld = gate_ld;
+    p.frame_row = frame_row; p.rows_per_frame = rows_per_frame > 0 ? rows_per_frame : 1;
+    p.M = M; p.N = N; p.K = K;
+    GemmOp op;
+    int rc = gemm_prepare(&op, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), ldw, p, epilogue, bn);
+    if (rc) return rc;
+    return gemm_run(&op, stream);
+}
+
+int gtav_ln_modulate(const void* x, void* out, int M, int D, const void* mod, int mod_ld, int shift_off, int scale_off,
+                     const int* frame_row, int rows_per_frame, gtav_stream_t stream) {
+    return launch_ln_modulate(static_cast<const bf16*>(x), static_cast<bf16*>(out), M, D, static_cast<const bf16*>(mod),
+                              mod_ld, shift_off, scale_off, frame_row, rows_per_frame, stream);
+}
+int gtav_ln_affine(const void* x, void* out, int M, int D, const float* w, const float* b, gtav_stream_t stream) {
+    return launch_ln_affine(static_cast<const bf16*>(x), static_cast<bf16*>(out), M, D, w, b, stream);
+}
+int gtav_attention_seq(const void* qkv, void* out, int groups, int seq, int heads, const float* rot, int rot_pairs,
+                       gtav_stream_t stream) {
+    return launch_attention_seq(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), groups, seq, heads,
+                                reinterpret_cast<const float2*>(rot), rot_pairs, stream);
+}
+int gtav_attention_temporal(const void* qkv, void* out, int B, int T, int positions, int heads, const float* rot,
+                            gtav_stream_t stream) {
+    return launch_attention_temporal(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), B, T, positions, heads,
+                                     reinterpret_cast<const float2*>(rot), stream);
+}
+int gtav_ddim_update(const float* x, const void* v_bf16, float* out, int F, int n, const float* abar_t,
+                     const float* abar_next, const int* final_flag, gtav_stream_t stream) {
+    return launch_ddim(x, static_cast<const bf16*>(v_bf16), out, F, n, abar_t, abar_next, final_flag, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,358 @@
+// bf16 GEMM for sm_100a: out[M,N] = epilogue(A[M,K] @ W[N,K]^T), fp32 accumulation in TMEM.
+//
+// Replaces every nn.Linear / patchify-conv on the hot path (reference model/attention.py:27-28,86-87;
+// model/dit.py:60-62,87-91,134,138,171-198; model/vae.py:65-67,147-152,192,214-215,233 and timm Mlp),
+// with the surrounding elementwise ops (bias, GELU/SiLU, adaLN gate, residual) fused as epilogues that
+// round to bf16 exactly where the reference's autocast graph does.
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0   : TMA producer  - cp.async.bulk.tensor 2-D tiles of A (128x64) and W (BNx64), 128B swizzle
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1)
+//   warps 2-5: epilogue      - tcgen05.ld 32x32b from their TMEM lane quadrant, fused math, 16-byte stores
+// smem full/empty mbarrier ring between producer and issuer; tcgen05.commit frees slots and signals
+// the epilogue.  Out-of-range rows / columns / K are zero-filled by TMA and masked in the epilogue.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gtav {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int GEMM_THREADS = 192;
+
+template <int BN, int STAGES>
+struct GemmSmem {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int BAR_OFF = STAGES * (A_BYTES + B_BYTES);
+    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;   // +1024: manual alignment slack
+};
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int col0, const uint32_t (&acc)[32],
+                                               const bf16* gate_row) {
+    // 32 consecutive columns of one output row, handled as 4 groups of 8 (16-byte vectors).
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int col = col0 + g * 8;
+        if (col >= p.N) break;                               // N is a multiple of 8
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(acc[g * 8 + j]);
+        if (EPI != EPI_STORE) {
+            uint4 bv = *reinterpret_cast<const uint4*>(p.bias + col);
+            const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 b2 = unpack_bf16x2(bw[j]);
+                y[2 * j] += b2.x;
+                y[2 * j + 1] += b2.y;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = bf16_round(y[j]);  // the Linear's own bf16 output
+        if (EPI == EPI_BIAS_GELU_TANH) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = gelu_tanh_f(y[j]);
+        } else if (EPI == EPI_BIAS_GELU_ERF) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = gelu_erf_f(y[j]);
+        } else if (EPI == EPI_BIAS_SILU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = silu_f(y[j]);
+        } else if (EPI == EPI_BIAS_GATE_RES || EPI == EPI_BIAS_RES || EPI == EPI_BIAS_RES_SILU) {
+            float r[8];
+            if (p.res != nullptr) {
+                uint4 rv = *reinterpret_cast<const uint4*>(p.res + static_cast<size_t>(row) * p.ldr + col);
+                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 r2 = unpack_bf16x2(rw[j]);
+                    r[2 * j] = r2.x;
+                    r[2 * j + 1] = r2.y;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[j] = 0.f;
+            }
+            if (EPI == EPI_BIAS_GATE_RES) {
+                uint4 gv = *reinterpret_cast<const uint4*>(gate_row + col);
+                const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 g2 = unpack_bf16x2(gw[j]);
+                    y[2 * j] = bf16_round(g2.x * y[2 * j]);
+                    y[2 * j + 1] = bf16_round(g2.y * y[2 * j + 1]);
+                }
+            }
+            if (EPI == EPI_BIAS_RES_SILU) {
+                if (p.res != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) y[j] = bf16_round(r[j] + y[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = silu_f(y[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = r[j] + y[j];
+            }
+        }
+        uint4 o;
+        o.x = pack_bf16x2(y[0], y[1]);
+        o.y = pack_bf16x2(y[2], y[3]);
+        o.z = pack_bf16x2(y[4], y[5]);
+        o.w = pack_bf16x2(y[6], y[7]);
+        *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(row) * p.ldo + col) = o;
+    }
+}
+
+template <int BN, int STAGES, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    using L = GemmSmem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * L::A_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_blk = blockIdx.x;
+    const int m_blk = blockIdx.y;
+    const int num_kb = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&empty_bar[s], 1);
+            }
+            mbar_init(accum_bar, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, BN);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full_bar[s], L::A_BYTES + L::B_BYTES);
+                tma_load_2d(sA + s * L::A_BYTES, &tmA, &full_bar[s], kb * BK, m_blk * BM);
+                tma_load_2d(sB + s * L::B_BYTES, &tmB, &full_bar[s], kb * BK, n_blk * BN);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tcgen05_fence_after();
+                const uint64_t da = umma_desc_sw128(smem_u32(sA + s * L::A_BYTES));
+                const uint64_t db = umma_desc_sw128(smem_u32(sB + s * L::B_BYTES));
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    // +32 bytes (16 bf16) along K inside the 128-byte swizzle row: +2 in 16-byte units
+                    umma_bf16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);       // slot reusable once these MMAs have read it
+            }
+            umma_commit(accum_bar);               // accumulator complete
+        }
+    } else {
+        const int q = warp & 3;                   // TMEM lane quadrant this warp may read
+        const int row = m_blk * BM + q * 32 + lane;
+        const bf16* gate_row = nullptr;
+        if (EPI == EPI_BIAS_GATE_RES && row < p.M) {
+            int f = row / p.rows_per_frame;
+            if (p.frame_row != nullptr) f = p.frame_row[f];
+            gate_row = p.gate + static_cast<size_t>(f) * p.gate_ld;
+        }
+        mbar_wait(accum_bar, 0);
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t acc[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, acc);
+            tmem_ld_wait();
+            const int col0 = n_blk * BN + c * 32;
+            if (row < p.M && col0 < p.N) epilogue_chunk<EPI>(p, row, col0, acc, gate_row);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// [rows, cols] bf16 row-major with leading dimension ld -> tiles of box_rows x 64, 128-byte swizzle.
+static int make_tmap(CUtensorMap* out, const bf16* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    EncodeTiledFn enc = encode_fn();
+    if (enc == nullptr) {
+        set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+        return -3;
+    }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld % 8) != 0) {
+        set_error("GEMM operand must be 16-byte aligned with a leading dimension multiple of 8 (ptr=%p ld=%llu)", ptr,
+                  (unsigned long long)ld);
+        return -1;
+    }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * sizeof(bf16)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box_rows=%u)", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+        return -3;
+    }
+    return 0;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+int gemm_prepare(GemmOp* op, const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi,
+                 int bn_override) {
+    if (p.M <= 0 || p.N <= 0 || p.K <= 0 || (p.N % 8) != 0 || (p.K % 8) != 0) {
+        set_error("gemm: unsupported shape M=%d N=%d K=%d (N and K must be positive multiples of 8)", p.M, p.N, p.K);
+        return -1;
+    }
+    if (epi < 0 || epi >= EPI_COUNT) {
+        set_error("gemm: unknown epilogue %d", epi);
+        return -1;
+    }
+    if (epi != EPI_STORE && p.bias == nullptr) {
+        set_error("gemm: epilogue %d needs a bias vector", epi);
+        return -1;
+    }
+    if (epi == EPI_BIAS_GATE_RES && (p.gate == nullptr || p.res == nullptr || p.rows_per_frame <= 0)) {
+        set_error("gemm: gated-residual epilogue needs gate, residual and rows_per_frame");
+        return -1;
+    }
+    if ((p.ldo % 8) != 0 || (p.res != nullptr && (p.ldr % 8) != 0) || (p.gate != nullptr && (p.gate_ld % 8) != 0)) {
+        set_error("gemm: output / residual / gate leading dimensions must be multiples of 8");
+        return -1;
+    }
+    const int m_tiles = (p.M + BM - 1) / BM;
+    int bn = bn_override;
+    if (bn == 0) {
+        if (p.N <= 64) bn = 64;
+        else if ((p.N % 256) == 0 && m_tiles * (p.N / 256) >= num_sms()) bn = 256;
+        else bn = 128;
+    }
+    if (bn != 64 && bn != 128 && bn != 256) {
+        set_error("gemm: tile width %d not in {64,128,256}", bn);
+        return -1;
+    }
+    op->p = p;
+    op->bn = bn;
+    op->epi = epi;
+    int rc = make_tmap(&op->tmA, A, p.M, p.K, lda, BM);
+    if (rc) return rc;
+    return make_tmap(&op->tmB, W, p.N, p.K, ldw, bn);
+}
+
+template <int BN, int STAGES, int EPI>
+static int launch_one(const GemmOp* op, cudaStream_t stream) {
+    using L = GemmSmem<BN, STAGES>;
+    static bool configured = false;
+    auto kern = gemm_bf16_kernel<BN, STAGES, EPI>;
+    if (!configured) {
+        GTAV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        configured = true;
+    }
+    dim3 grid((op->p.N + BN - 1) / BN, (op->p.M + BM - 1) / BM, 1);
+    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(op->tmA, op->tmB, op->p);
+    GTAV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <int EPI>
+static int launch_epi(const GemmOp* op, cudaStream_t stream) {
+    switch (op->bn) {
+        case 64: return launch_one<64, 4, EPI>(op, stream);
+        case 128: return launch_one<128, 3, EPI>(op, stream);
+        default: return launch_one<256, 4, EPI>(op, stream);
+    }
+}
+
+int gemm_run(const GemmOp* op, cudaStream_t stream) {
+    switch (op->epi) {
+        case EPI_STORE: return launch_epi<EPI_STORE>(op, stream);
+        case EPI_BIAS: return launch_epi<EPI_BIAS>(op, stream);
+        case EPI_BIAS_GELU_TANH: return launch_epi<EPI_BIAS_GELU_TANH>(op, stream);
+        case EPI_BIAS_GELU_ERF: return launch_epi<EPI_BIAS_GELU_ERF>(op, stream);
+        case EPI_BIAS_SILU: return launch_epi<EPI_BIAS_SILU>(op, stream);
+        case EPI_BIAS_GATE_RES: return launch_epi<EPI_BIAS_GATE_RES>(op, stream);
+        case EPI_BIAS_RES: return launch_epi<EPI_BIAS_RES>(op, stream);
+        case EPI_BIAS_RES_SILU: return launch_epi<EPI_BIAS_RES_SILU>(op, stream);
+    }
+    set_error("gemm: unknown epilogue %d", op->epi);
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// error text
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+}  // namespace gtav

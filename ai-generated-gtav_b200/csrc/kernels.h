@@ -1,0 +1,102 @@
+// Internal host-side interface between the engines (dit_engine.cu, vae_engine.cu, sampler.cu) and
+// the kernel translation units.  Nothing here is exported; the C ABI lives in include/gtav_b200.h.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gtav {
+
+typedef __nv_bfloat16 bf16;
+
+// thread-local error text returned by gtav_last_error()
+void set_error(const char* fmt, ...);
+const char* get_error();
+#define GTAV_CUDA_OK(expr)                                                                     \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            gtav::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return -2;                                                                         \
+        }                                                                                      \
+    } while (0)
+
+// ---------------------------------------------------------------- GEMM (gemm_sm100.cu)
+enum Epilogue : int {
+    EPI_STORE = 0,           // out = bf16(acc)
+    EPI_BIAS = 1,            // out = bf16(acc + b)
+    EPI_BIAS_GELU_TANH = 2,  // out = bf16(gelu_tanh(bf16(acc + b)))
+    EPI_BIAS_GELU_ERF = 3,   // out = bf16(gelu_erf(bf16(acc + b)))
+    EPI_BIAS_SILU = 4,       // out = bf16(silu(bf16(acc + b)))
+    EPI_BIAS_GATE_RES = 5,   // out = bf16(res + bf16(gate * bf16(acc + b)))
+    EPI_BIAS_RES = 6,        // out = bf16(res + bf16(acc + b))
+    EPI_BIAS_RES_SILU = 7,   // out = bf16(silu(bf16(res + bf16(acc + b))))   (res may be null)
+    EPI_COUNT = 8
+};
+
+struct GemmParams {
+    bf16* out; int ldo;
+    const bf16* bias;
+    const bf16* res; int ldr;
+    const bf16* gate; int gate_ld;      // gate vector of row r: gate + frame_row[r / rows_per_frame] * gate_ld
+    const int* frame_row;               // null => identity
+    int rows_per_frame;
+    int M, N, K;
+};
+
+struct GemmOp {
+    CUtensorMap tmA, tmB;
+    GemmParams p;
+    int bn;      // tile width chosen at prepare time (64 / 128 / 256)
+    int epi;
+};
+
+// out[M,N] = epilogue(A[M,K] @ W[N,K]^T); A, W row-major bf16 with leading dimensions lda / ldw
+// (elements, multiples of 8; base pointers 16-byte aligned).  bn_override = 0 picks the tile width.
+int gemm_prepare(GemmOp* op, const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi,
+                 int bn_override = 0);
+int gemm_run(const GemmOp* op, cudaStream_t stream);
+
+// ---------------------------------------------------------------- row kernels (norm_mod.cu)
+// out = bf16( LN(x) * bf16(1 + bf16(scale + 1e-6)) + shift ), LN without affine, eps 1e-6.
+// shift/scale of row r live at mod + frame_row[r / rows_per_frame] * mod_ld + {shift_off, scale_off}.
+int launch_ln_modulate(const bf16* x, bf16* out, int M, int D, const bf16* mod, int mod_ld, int shift_off,
+                       int scale_off, const int* frame_row, int rows_per_frame, cudaStream_t s);
+// out = bf16( LN(x) * w + b ), fp32 affine parameters (VAE).
+int launch_ln_affine(const bf16* x, bf16* out, int M, int D, const float* w, const float* b, cudaStream_t s);
+
+// ---------------------------------------------------------------- attention (attn_mma.cu, attn_temporal.cu)
+// qkv [rows, 3*H*64] (q | k | v, head-major inside each), out [rows, H*64].  One problem per
+// (group of `seq` consecutive rows, head).  rot: float2 (cos, sin) [seq][rot_pairs] applied to the
+// first 2*rot_pairs features of q and k.  seq must be 144 (DiT spatial) or 576 (VAE).
+int launch_attention_seq(const bf16* qkv, bf16* out, int groups, int seq, int heads, const float2* rot, int rot_pairs,
+                         cudaStream_t s);
+// Causal attention over the T frames of each (b, spatial position, head); rows ordered (b, t, pos).
+// rot: float2 [T][32] window-relative angles.
+int launch_attention_temporal(const bf16* qkv, bf16* out, int B, int T, int positions, int heads, const float2* rot,
+                              cudaStream_t s);
+
+// ---------------------------------------------------------------- conditioning / patches / sampler (elementwise.cu)
+// temb[r, 0:128] = cos(t_r f), temb[r,128:256] = sin(t_r f) (bf16); aemb[r,:] = bf16(act_r @ Wa^T + ba) if actions.
+int launch_cond_prep(const int64_t* t, const float* actions, int act_dim, int R, const float* freqs, const bf16* Wa,
+                     const bf16* ba, bf16* temb, bf16* aemb, int D, cudaStream_t s);
+// x [F, C, H, W] (fp32 or bf16) -> patches [F*(H/p)*(W/p), ldo] bf16, k = c*p*p + ph*p + pw, zero padded to ldo.
+int launch_patchify(const void* x, int x_is_bf16, bf16* out, int ldo, int F, int C, int H, int W, int p, float scale,
+                    cudaStream_t s);
+// DiT un-patchify: y [F*gh*gw, p*p*C] -> v [F, C, gh*p, gw*p] bf16, feature = ph*(p*C) + pw*C + c.
+int launch_dit_unpatchify(const bf16* y, bf16* out, int F, int C, int gh, int gw, int p, cudaStream_t s);
+// VAE un-patchify: y [F*sh*sw, 3*p*p] -> img [F,3,sh*p,sw*p] bf16 (feature = c*p*p + ph*p + pw), or, with
+// to_u8, the fused pixel epilogue of generate.py:241-244 -> uint8 [F, sh*p, sw*p, 3].
+int launch_vae_unpatchify(const bf16* y, void* out, int to_u8, int F, int sh, int sw, int p, cudaStream_t s);
+// z [rows, C] float (scaled by `scale`) -> bf16 [rows, ldo] zero padded.
+int launch_cast_pad(const float* z, bf16* out, int rows, int C, int ldo, float scale, cudaStream_t s);
+// moments [rows, ldm] bf16 -> mean [rows, C] float (= first C columns), times `scale` rounded to bf16 if round_bf16.
+int launch_take_mean(const bf16* moments, int ldm, float* out, int rows, int C, float scale, int round_bf16,
+                     cudaStream_t s);
+// v-prediction DDIM update (train_dit.py:110-123) over frames: x, v, out [F, n] ; abar_t / abar_next per frame;
+// `final` selects the x0 return of noise_idx <= 0.
+int launch_ddim(const float* x, const bf16* v, float* out, int F, int n, const float* abar_t, const float* abar_next,
+                const int* final_flag, cudaStream_t s);
+
+}  // namespace gtav

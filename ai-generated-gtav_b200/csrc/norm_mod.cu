@@ -1,0 +1,115 @@
+// Row kernels: LayerNorm fused with adaLN modulate (DiT) or with the affine transform (VAE).
+//
+// Replaces `modulate(norm(x), shift, scale)` (reference model/dit.py:19-27 with the LayerNorms of
+// 133,163,170,181,189) and the affine LayerNorms of the VAE blocks (model/vae.py:155-156,313,331).
+// HBM/L2-bound: one warp per 1024-wide row, 16-byte loads/stores, fp32 statistics (two-pass in
+// registers), output rounded once to bf16 - the rounding the following Linear's autocast applies.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gtav {
+
+static constexpr int LN_WARPS = 8;
+
+// D = 32 lanes * 8 elements * CHUNKS
+template <int CHUNKS, bool AFFINE>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_rows_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int M, const bf16* __restrict__ mod, int mod_ld,
+               int shift_off, int scale_off, const int* __restrict__ frame_row, int rows_per_frame,
+               const float* __restrict__ w, const float* __restrict__ b) {
+    constexpr int D = CHUNKS * 256;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const bf16* xr = x + static_cast<size_t>(row) * D;
+    float v[CHUNKS][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        uint4 u = *reinterpret_cast<const uint4*>(xr + c * 256 + lane * 8);
+        const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f = unpack_bf16x2(uw[j]);
+            v[c][2 * j] = f.x;
+            v[c][2 * j + 1] = f.y;
+            sum += f.x + f.y;
+        }
+    }
+    const float mean = warp_sum(sum) * (1.0f / D);
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d = v[c][j] - mean;
+            sq += d * d;
+        }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + 1e-6f);
+
+    const bf16* mrow = nullptr;
+    if (!AFFINE) {
+        int f = row / rows_per_frame;
+        if (frame_row != nullptr) f = frame_row[f];
+        mrow = mod + static_cast<size_t>(f) * mod_ld;
+    }
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int col = c * 256 + lane * 8;
+        float y[8];
+        if (AFFINE) {
+            const float4 w0 = *reinterpret_cast<const float4*>(w + col), w1 = *reinterpret_cast<const float4*>(w + col + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(b + col), b1 = *reinterpret_cast<const float4*>(b + col + 4);
+            const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = (v[c][j] - mean) * rstd * ww[j] + bb[j];
+        } else {
+            const uint4 sh = *reinterpret_cast<const uint4*>(mrow + shift_off + col);
+            const uint4 sc = *reinterpret_cast<const uint4*>(mrow + scale_off + col);
+            const uint32_t shw[4] = {sh.x, sh.y, sh.z, sh.w}, scw[4] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 s2 = unpack_bf16x2(shw[j]), c2 = unpack_bf16x2(scw[j]);
+                // scale + 1e-6 and 1 + scale are bf16 tensor ops in the reference (model/dit.py:26-27)
+                const float m0 = bf16_round(1.0f + bf16_round(c2.x + 1e-6f));
+                const float m1 = bf16_round(1.0f + bf16_round(c2.y + 1e-6f));
+                y[2 * j] = (v[c][2 * j] - mean) * rstd * m0 + s2.x;
+                y[2 * j + 1] = (v[c][2 * j + 1] - mean) * rstd * m1 + s2.y;
+            }
+        }
+        uint4 o;
+        o.x = pack_bf16x2(y[0], y[1]);
+        o.y = pack_bf16x2(y[2], y[3]);
+        o.z = pack_bf16x2(y[4], y[5]);
+        o.w = pack_bf16x2(y[6], y[7]);
+        *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * D + col) = o;
+    }
+}
+
+int launch_ln_modulate(const bf16* x, bf16* out, int M, int D, const bf16* mod, int mod_ld, int shift_off,
+                       int scale_off, const int* frame_row, int rows_per_frame, cudaStream_t s) {
+    if (D != 1024 || (mod_ld % 8) || (shift_off % 8) || (scale_off % 8) || rows_per_frame <= 0) {
+        set_error("ln_modulate: unsupported D=%d mod_ld=%d offsets=%d,%d", D, mod_ld, shift_off, scale_off);
+        return -1;
+    }
+    if (M <= 0) return 0;
+    ln_rows_kernel<4, false><<<(M + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, s>>>(
+        x, out, M, mod, mod_ld, shift_off, scale_off, frame_row, rows_per_frame, nullptr, nullptr);
+    GTAV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_ln_affine(const bf16* x, bf16* out, int M, int D, const float* w, const float* b, cudaStream_t s) {
+    if (D != 1024) {
+        set_error("ln_affine: unsupported D=%d", D);
+        return -1;
+    }
+    if (M <= 0) return 0;
+    ln_rows_kernel<4, true><<<(M + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, s>>>(x, out, M, nullptr, 0, 0, 0, nullptr, 1,
+                                                                                  w, b);
+    GTAV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace gtav
