@@ -18,6 +18,8 @@ EXPORTS = [
     "gtav_dit_mod_width", "gtav_dit_workspace_bytes", "gtav_dit_plan_create", "gtav_dit_plan_destroy",
     "gtav_dit_conditioning", "gtav_dit_backbone", "gtav_dit_forward", "gtav_vae_create", "gtav_vae_destroy",
     "gtav_vae_workspace_bytes", "gtav_vae_plan_create", "gtav_vae_plan_destroy", "gtav_vae_encode", "gtav_vae_decode",
+    "gtav_sampler_cond_rows", "gtav_sampler_scratch_bytes", "gtav_sampler_create", "gtav_sampler_destroy",
+    "gtav_sampler_run_frame", "gtav_noise_clamp",
 ]
 
 vp = C.c_void_p
@@ -93,6 +95,11 @@ def load() -> C.CDLL:
         "gtav_vae_plan_destroy": [vp],
         "gtav_vae_encode": [vp, vp, i, fp, C.c_float, i, vp],
         "gtav_vae_decode": [vp, fp, C.c_float, vp, i, vp],
+        "gtav_sampler_cond_rows": [i, i, i],
+        "gtav_sampler_create": [vp, i, i, i, i, fp, vp, fp, ip, vp, sz, i, vp, C.POINTER(vp)],
+        "gtav_sampler_destroy": [vp],
+        "gtav_sampler_run_frame": [vp, i, vp],
+        "gtav_noise_clamp": [fp, fp, C.c_long, i, i, C.c_float, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -102,6 +109,8 @@ def load() -> C.CDLL:
     lib.gtav_dit_workspace_bytes.restype = sz
     lib.gtav_vae_workspace_bytes.argtypes = [vp, i]
     lib.gtav_vae_workspace_bytes.restype = sz
+    lib.gtav_sampler_scratch_bytes.argtypes = [i, i, i]
+    lib.gtav_sampler_scratch_bytes.restype = sz
     _lib = lib
     return lib
 

@@ -262,7 +262,7 @@ int gtav_attention_temporal(const void* qkv, void* out, int B, int T, int positi
 }
 int gtav_ddim_update(const float* x, const void* v_bf16, float* out, int F, int n, const float* abar_t,
                      const float* abar_next, const int* final_flag, gtav_stream_t stream) {
-    return launch_ddim(x, static_cast<const bf16*>(v_bf16), out, F, n, abar_t, abar_next, final_flag, stream);
+    return launch_ddim(x, n, static_cast<const bf16*>(v_bf16), n, out, n, F, n, abar_t, abar_next, final_flag, stream);
 }
 
 }  // extern "C"

@@ -197,9 +197,9 @@ int launch_take_mean(const bf16* moments, int ldm, float* out, int rows, int C, 
 // the reference's tensor expression; _rn intrinsics keep nvcc from contracting into FMAs so the
 // result is bit-identical to the separate torch kernels.
 // ------------------------------------------------------------------------------------------
-__global__ void ddim_kernel(const float* __restrict__ x, const bf16* __restrict__ v, float* __restrict__ out, int n,
-                            const float* __restrict__ abar_t, const float* __restrict__ abar_next,
-                            const int* __restrict__ final_flag) {
+__global__ void ddim_kernel(const float* __restrict__ x, long x_stride, const bf16* __restrict__ v, long v_stride,
+                            float* __restrict__ out, long out_stride, int n, const float* __restrict__ abar_t,
+                            const float* __restrict__ abar_next, const int* __restrict__ final_flag) {
     const int f = blockIdx.y;
     const float a = abar_t[f], an = abar_next[f];
     const float c_x = sqrtf(a), c_v = sqrtf(__fsub_rn(1.0f, a));
@@ -208,22 +208,80 @@ __global__ void ddim_kernel(const float* __restrict__ x, const bf16* __restrict_
     const float c_n0 = sqrtf(an), c_ne = sqrtf(__fsub_rn(1.0f, an));
     const bool fin = (*final_flag) != 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const size_t o = static_cast<size_t>(f) * n + i;
-        const float xv = x[o], vv = __bfloat162float(v[o]);
+        const float xv = x[f * x_stride + i], vv = __bfloat162float(v[f * v_stride + i]);
         const float x0 = __fsub_rn(__fmul_rn(c_x, xv), __fmul_rn(c_v, vv));
         float r = x0;
         if (!fin) {
             const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(c_ix, xv), x0), c_den);
             r = __fadd_rn(__fmul_rn(c_n0, x0), __fmul_rn(c_ne, eps));
         }
-        out[o] = r;
+        out[f * out_stride + i] = r;
     }
 }
 
-int launch_ddim(const float* x, const bf16* v, float* out, int F, int n, const float* abar_t, const float* abar_next,
-                const int* final_flag, cudaStream_t s) {
+int launch_ddim(const float* x, long x_stride, const bf16* v, long v_stride, float* out, long out_stride, int F, int n,
+                const float* abar_t, const float* abar_next, const int* final_flag, cudaStream_t s) {
     if (F <= 0 || n <= 0) return 0;
-    ddim_kernel<<<dim3((n + 255) / 256, F), 256, 0, s>>>(x, v, out, n, abar_t, abar_next, final_flag);
+    ddim_kernel<<<dim3((n + 255) / 256, F), 256, 0, s>>>(x, x_stride, v, v_stride, out, out_stride, n, abar_t, abar_next,
+                                                        final_flag);
+    GTAV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace gtav
+
+namespace gtav {
+
+// ------------------------------------------------------------------------------------------
+// Per-step sampler bookkeeping (replaces the host-side torch.full / indexing of train_dit.py:64-99,
+// 110,116-117).  Conditioning-table row layout: context frame j of rollout b -> b*(T-1)+j;
+// last frame of rollout b at step k -> B*(T-1) + b*(steps+1) + k.
+// ------------------------------------------------------------------------------------------
+__global__ void step_prep_kernel(int* counter, const int* __restrict__ levels, const float* __restrict__ abar, int B,
+                                 int T, int steps, int* __restrict__ frame_row, float* __restrict__ abar_t,
+                                 float* __restrict__ abar_next, int* __restrict__ final_flag) {
+    const int k = *counter;
+    __syncthreads();
+    for (int f = threadIdx.x; f < B * T; f += blockDim.x) {
+        const int b = f / T, j = f % T;
+        frame_row[f] = (j < T - 1) ? b * (T - 1) + j : B * (T - 1) + b * (steps + 1) + k;
+    }
+    const float at = abar[levels[k]], an = abar[levels[k > 0 ? k - 1 : 0]];
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        abar_t[b] = at;
+        abar_next[b] = an;
+    }
+    if (threadIdx.x == 0) {
+        *final_flag = k <= 0 ? 1 : 0;
+        *counter = k - 1;
+    }
+}
+
+int launch_step_prep(int* counter, const int* levels, const float* abar, int B, int T, int steps, int* frame_row,
+                     float* abar_t, float* abar_next, int* final_flag, cudaStream_t s) {
+    step_prep_kernel<<<1, 256, 0, s>>>(counter, levels, abar, B, T, steps, frame_row, abar_t, abar_next, final_flag);
+    GTAV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+__global__ void set_int_kernel(int* dst, int value) { *dst = value; }
+
+int launch_set_int(int* dst, int value, cudaStream_t s) {
+    set_int_kernel<<<1, 1, 0, s>>>(dst, value);
+    GTAV_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+__global__ void noise_clamp_kernel(const float* __restrict__ noise, float* __restrict__ x, long x_stride, int n,
+                                   float amax) {
+    const int f = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        x[f * x_stride + i] = fminf(fmaxf(noise[static_cast<long>(f) * n + i], -amax), amax);
+}
+
+int launch_noise_clamp(const float* noise, float* x, long x_stride, int F, int n, float amax, cudaStream_t s) {
+    if (F <= 0 || n <= 0) return 0;
+    noise_clamp_kernel<<<dim3((n + 255) / 256, F), 256, 0, s>>>(noise, x, x_stride, n, amax);
     GTAV_CUDA_OK(cudaGetLastError());
     return 0;
 }

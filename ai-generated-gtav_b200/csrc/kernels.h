@@ -94,9 +94,16 @@ int launch_cast_pad(const float* z, bf16* out, int rows, int C, int ldo, float s
 // moments [rows, ldm] bf16 -> mean [rows, C] float (= first C columns), times `scale` rounded to bf16 if round_bf16.
 int launch_take_mean(const bf16* moments, int ldm, float* out, int rows, int C, float scale, int round_bf16,
                      cudaStream_t s);
-// v-prediction DDIM update (train_dit.py:110-123) over frames: x, v, out [F, n] ; abar_t / abar_next per frame;
-// `final` selects the x0 return of noise_idx <= 0.
-int launch_ddim(const float* x, const bf16* v, float* out, int F, int n, const float* abar_t, const float* abar_next,
-                const int* final_flag, cudaStream_t s);
+// v-prediction DDIM update (train_dit.py:110-123) over F frames of n elements (frame f at ptr + f*stride);
+// abar_t / abar_next per frame; *final_flag selects the x0 return of noise_idx <= 0.
+int launch_ddim(const float* x, long x_stride, const bf16* v, long v_stride, float* out, long out_stride, int F, int n,
+                const float* abar_t, const float* abar_next, const int* final_flag, cudaStream_t s);
+// Sampler bookkeeping for one DDIM step, read from / written to device memory so a captured graph can be
+// replayed: k = *counter; frame_row, abar_t, abar_next, final_flag for step k; *counter = k - 1.
+int launch_step_prep(int* counter, const int* levels, const float* abar, int B, int T, int steps, int* frame_row,
+                     float* abar_t, float* abar_next, int* final_flag, cudaStream_t s);
+int launch_set_int(int* dst, int value, cudaStream_t s);
+// x[f*stride + i] = clamp(noise[f*n + i], -amax, amax)  (generate.py:201-203)
+int launch_noise_clamp(const float* noise, float* x, long x_stride, int F, int n, float amax, cudaStream_t s);
 
 }  // namespace gtav

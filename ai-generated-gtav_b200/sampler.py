@@ -1,0 +1,165 @@
+"""Whole-rollout sampler: the autoregressive loop of reference generate.py:186-244 driven through the
+C ABI with one CUDA-graph replay per DDIM step.
+
+    s = Sampler(dit, vae, noise_steps=100)
+    frames_u8, latents = s.generate(prompt_video, actions, total_frames=32)
+
+Semantics are the reference's: context frames at t = stabilization_level, last frame walks
+linspace(0, 999, steps+1) truncated to integers from the top, steps+1 DiT evaluations per frame, only
+the last frame of the window is updated, new frames start from clamp(randn, +-noise_abs_max), frames are
+decoded with the pixel epilogue of generate.py:241-244.  What differs is scheduling only:
+  * B independent rollouts per call (the reference hard-codes B = 1, generate.py:133);
+  * the adaLN conditioning table of a frame is computed once per frame instead of once per step
+    (it depends on (t, action) only - an exact hoist);
+  * no host work per step: timestep rows and DDIM coefficients are derived on the device.
+Noise comes from torch (`torch.randn` on the rollout's device, as generate.py:201) unless the caller
+supplies it, so a seeded torch generator reproduces a run.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+try:
+    from . import _native as N
+    from .utils import sigmoid_beta_schedule
+except ImportError:
+    import _native as N
+    from utils import sigmoid_beta_schedule
+
+SCALING_FACTOR = 0.07843137255   # generate.py:51,241
+
+
+class Sampler:
+    def __init__(self, dit, vae=None, noise_steps: int = 100, stabilization_level: int = 15, noise_abs_max: float = 20.0,
+                 max_noise_level: int = 1000, use_graph: bool = True):
+        self.dit, self.vae = dit, vae
+        self.steps = int(noise_steps)
+        self.stab = int(stabilization_level)
+        self.noise_abs_max = float(noise_abs_max)
+        self.use_graph = bool(use_graph)
+        self.levels = [int(v) for v in torch.linspace(0, max_noise_level - 1, self.steps + 1).tolist()]
+        betas = sigmoid_beta_schedule(max_noise_level).float()
+        self.abar_host = torch.cumprod(1.0 - betas, dim=0)
+        self._ctx = {}          # (B, T) -> dict(sampler handle, buffers)
+        self._stream = None
+        self.frame_elems = dit.in_channels * dit.input_h * dit.input_w
+
+    # ------------------------------------------------------------------ per-(B,T) context
+    def _context(self, B, T, dev):
+        key = (B, T)
+        if key in self._ctx:
+            return self._ctx[key]
+        lib = N.load()
+        self.dit._pack()
+        rows = lib.gtav_sampler_cond_rows(B, T, self.steps)
+        plan = self.dit._plan(B, T, rows)
+        n = self.frame_elems
+        x_win = torch.zeros((B, T, n), dtype=torch.float32, device=dev)
+        v_out = torch.zeros((B, T, n), dtype=torch.bfloat16, device=dev)
+        scratch = torch.zeros(lib.gtav_sampler_scratch_bytes(B, T, self.steps) + 256, dtype=torch.uint8, device=dev)
+        sbase = (scratch.data_ptr() + 255) & ~255
+        abar = self.abar_host.to(dev)
+        levels = (C.c_int * (self.steps + 1))(*self.levels)
+        h = N.vp()
+        N.check(lib.gtav_sampler_create(plan, B, T, self.steps, n, x_win.data_ptr(), v_out.data_ptr(), abar.data_ptr(), levels,
+                                        sbase, scratch.numel() - 256, int(self.use_graph), N.current_stream(), C.byref(h)),
+                "gtav_sampler_create")
+        ctx = dict(h=h, plan=plan, x_win=x_win, v_out=v_out, scratch=scratch, abar=abar, rows=rows)
+        self._ctx[key] = ctx
+        return ctx
+
+    def close(self):
+        lib = N.load()
+        for ctx in self._ctx.values():
+            lib.gtav_sampler_destroy(ctx["h"])
+        self._ctx = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ conditioning rows of one frame
+    def _cond_inputs(self, B, T, i, start, actions, dev):
+        """t [rows] int64 and actions [rows, A] for the table layout of gtav_sampler_cond_rows."""
+        S1 = self.steps + 1
+        t_ctx = torch.full((B * (T - 1),), self.stab, dtype=torch.long, device=dev)
+        t_last = torch.tensor(self.levels, dtype=torch.long, device=dev).repeat(B)
+        t = torch.cat([t_ctx, t_last])
+        if actions is None:
+            return t, None
+        a_ctx = actions[:, start:start + T - 1].reshape(B * (T - 1), -1)
+        a_last = actions[:, start + T - 1].unsqueeze(1).expand(B, S1, -1).reshape(B * S1, -1)
+        return t, torch.cat([a_ctx, a_last]).to(torch.float32).contiguous()
+
+    # ------------------------------------------------------------------ latents -> latents
+    @torch.no_grad()
+    def sample_latents(self, prompt_latents, actions, total_frames, noise=None, generator=None, steps_limit=None,
+                       on_frame=None):
+        """prompt_latents [B, n_prompt, C, h, w] -> fp32 latents [B, total_frames, C, h, w].
+        noise: optional [B, total_frames - n_prompt, C, h, w] (unclamped N(0,1) draws)."""
+        N.require_cuda(prompt_latents, "prompt_latents")
+        lib = N.load()
+        dev = prompt_latents.device
+        B, n_prompt = prompt_latents.shape[:2]
+        shape = tuple(prompt_latents.shape[2:])
+        n = self.frame_elems
+        if actions is not None:
+            actions = actions.to(dev)
+        x = torch.zeros((B, total_frames, n), dtype=torch.float32, device=dev)
+        x[:, :n_prompt] = prompt_latents.reshape(B, n_prompt, n).float()
+        if self.use_graph and self._stream is None:
+            self._stream = torch.cuda.Stream(device=dev)     # graph capture needs a non-default stream
+        stream = self._stream if self.use_graph else torch.cuda.current_stream(dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.device(dev), torch.cuda.stream(stream):
+            for i in range(n_prompt, total_frames):
+                start = max(0, i + 1 - self.dit.max_frames)
+                T = i + 1 - start
+                ctx = self._context(B, T, dev)
+                if noise is not None:
+                    chunk = noise[:, i - n_prompt].to(device=dev, dtype=torch.float32).reshape(B, n).contiguous()
+                else:
+                    chunk = torch.randn((B, n), device=dev, generator=generator)
+                xw = ctx["x_win"]
+                xw[:, : T - 1] = x[:, start:i]
+                N.check(lib.gtav_noise_clamp(chunk.data_ptr(), xw.data_ptr() + (T - 1) * n * 4, T * n, B, n,
+                                             self.noise_abs_max, stream.cuda_stream), "gtav_noise_clamp")
+                t_rows, a_rows = self._cond_inputs(B, T, i, start, actions, dev)
+                N.check(lib.gtav_dit_conditioning(ctx["plan"], t_rows.data_ptr(), N.ptr(a_rows), stream.cuda_stream),
+                        "gtav_dit_conditioning")
+                N.check(lib.gtav_sampler_run_frame(ctx["h"], -1 if steps_limit is None else int(steps_limit),
+                                                   stream.cuda_stream), "gtav_sampler_run_frame")
+                x[:, i] = xw[:, T - 1]
+                if on_frame is not None:
+                    on_frame(i, x)
+        torch.cuda.current_stream(dev).wait_stream(stream)
+        return x.reshape(B, total_frames, *shape)
+
+    # ------------------------------------------------------------------ pixels -> pixels
+    @torch.no_grad()
+    def encode_prompt(self, video):
+        """video [B, n, 3, H, W] in [0,1] -> latents [B, n, C, h, w] (generate.py:50-66 `vae_encode`)."""
+        B, n = video.shape[:2]
+        vae = self.vae
+        frames = video.reshape(B * n, *video.shape[2:])
+        mean = vae.encode_mean(frames * 2 - 1, scale=SCALING_FACTOR, round_bf16=True)
+        return mean.reshape(B, n, vae.seq_h, vae.seq_w, vae.latent_dim).permute(0, 1, 4, 2, 3).contiguous()
+
+    @torch.no_grad()
+    def decode_frames(self, latents, chunk: int = 32):
+        """latents [B, F, C, h, w] -> uint8 [B, F, H, W, 3] (generate.py:238-244)."""
+        B, F = latents.shape[:2]
+        vae = self.vae
+        z = latents.permute(0, 1, 3, 4, 2).reshape(B * F, vae.seq_len, vae.latent_dim).float().contiguous()
+        outs = [vae.decode(z[s:s + chunk], divisor=SCALING_FACTOR, to_uint8=True) for s in range(0, B * F, chunk)]
+        return torch.cat(outs).reshape(B, F, vae.input_height, vae.input_width, 3)
+
+    @torch.no_grad()
+    def generate(self, prompt_video, actions, total_frames, noise=None, generator=None):
+        lat = self.encode_prompt(prompt_video)
+        lat = self.sample_latents(lat, actions, total_frames, noise=noise, generator=generator)
+        return self.decode_frames(lat), lat

@@ -173,6 +173,30 @@ int gtav_vae_encode(gtav_vae_plan_t p, const void* img, int img_is_bf16, float* 
  * or uint8 [N,H,W,3] with the pixel epilogue of generate.py:241-244 fused (to_u8 = 1). */
 int gtav_vae_decode(gtav_vae_plan_t p, const float* z, float divisor, void* out, int to_u8, gtav_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Sampler (stands in for the per-frame loop of generate.py:204-220 around train_dit.py:30-125)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gtav_sampler_s* gtav_sampler_t;
+
+/* Rows of the per-frame conditioning table a sampler plan needs: B*(T-1) context rows (row b*(T-1)+j for
+ * window frame j of rollout b, t = stabilisation level) followed by B*(steps+1) last-frame rows
+ * (row B*(T-1) + b*(steps+1) + k for noise level k).  Create the DiT plan with this cond_rows and fill the
+ * table with gtav_dit_conditioning once per generated frame. */
+int gtav_sampler_cond_rows(int B, int T, int steps);
+size_t gtav_sampler_scratch_bytes(int B, int T, int steps);
+/* x_win: fp32 [B,T,frame_elems] window (caller loads context frames + clamped noise before each frame);
+ * v_out: bf16 [B,T,frame_elems]; abar_dev: fp32 alphas_cumprod on device; levels_host: int[steps+1] integer
+ * timesteps (linspace(0,999,steps+1) truncated).  This call synchronises `stream` once (copies levels). */
+int gtav_sampler_create(gtav_dit_plan_t plan, int B, int T, int steps, int frame_elems, float* x_win, void* v_out,
+                        const float* abar_dev, const int* levels_host, void* scratch, size_t scratch_bytes, int use_graph,
+                        gtav_stream_t stream, gtav_sampler_t* out);
+void gtav_sampler_destroy(gtav_sampler_t s);
+/* Runs noise levels steps, steps-1, ..., down to (steps+1-n_steps) on the window (n_steps < 0: all steps+1).
+ * With use_graph the step is captured once (stream must not be the legacy default stream) and replayed. */
+int gtav_sampler_run_frame(gtav_sampler_t s, int n_steps, gtav_stream_t stream);
+/* x[f*x_stride + i] = clamp(noise[f*n + i], -amax, +amax): the fresh frame of generate.py:201-203. */
+int gtav_noise_clamp(const float* noise, float* x, long x_stride, int F, int n, float amax, gtav_stream_t stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -1,10 +1,18 @@
 #!/bin/bash
-# One gpurun call: kernel tests, model parity, micro-benchmarks.  Each stage in its own process with a
+# One gpurun call: GPU tests, smoke, bench, ncu launch list.  Each stage in its own process with a
 # timeout so a trapped kernel cannot take the rest down.  Logs land in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
-run() { name=$1; shift; echo "=== $name" ; timeout "${TMO:-600}" "$@" > gpurun_out/$name.log 2>&1; echo "exit $?"; tail -${TAILN:-25} gpurun_out/$name.log; }
-TAILN=40 run t_gemm python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "gemm" --no-header -p no:cacheprovider
-TAILN=30 run t_kernels python -m pytest tests/test_kernels_gpu.py -m gpu -q -k "not gemm" --no-header -p no:cacheprovider
-TAILN=60 run t_model python -m pytest tests/test_model_gpu.py -m gpu -q -s --no-header -p no:cacheprovider
-TAILN=40 run b_kernels python scripts/bench_kernels.py
+run() { name=$1; shift; echo "=== $name" ; timeout "${TMO:-900}" "$@" > gpurun_out/$name.log 2>&1; echo "exit $?"; tail -${TAILN:-25} gpurun_out/$name.log; }
+STAGES=${STAGES:-"tests smoke bench ncu"}
+for st in $STAGES; do
+case $st in
+tests) TAILN=30 run t_all python -m pytest tests -m gpu -q -s --no-header -p no:cacheprovider ;;
+smoke) TAILN=5 run smoke python -c "import __graft_entry__ as g; g.smoke()" ;;
+bench) TAILN=5 run bench python bench.py ;;
+bench_c3) TAILN=5 run bench_c3 python bench.py --workload c3 --steps 1 --warmup 1 --no-cpu-baseline ;;
+kbench) TAILN=40 run b_kernels python scripts/bench_kernels.py ;;
+ncu) TAILN=3 run ncu_list ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --workload c1 --steps 1 --warmup 1 --no-cpu-baseline ;;
+ncu_full) TAILN=3 run ncu_full ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 200 -c 4 -o gpurun_out/prof_gemm python bench.py --workload c1 --steps 1 --warmup 1 --no-cpu-baseline ;;
+esac
+done
