@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libgtav_b200.so")
 
 # every symbol include/gtav_b200.h declares (tests check the .so exports exactly these)
 EXPORTS = [
-    "gtav_last_error", "gtav_abi_version", "gtav_gemm_bf16", "gtav_ln_modulate", "gtav_ln_affine",
+    "gtav_last_error", "gtav_abi_version", "gtav_gemm_bf16", "gtav_gemm_skinny_bf16", "gtav_gemm_skinny_workspace_bytes",
+    "gtav_dit_context", "gtav_dit_last_frame", "gtav_attention_temporal_last", "gtav_ln_modulate", "gtav_ln_affine",
     "gtav_attention_seq", "gtav_attention_temporal", "gtav_ddim_update", "gtav_dit_create", "gtav_dit_destroy",
     "gtav_dit_mod_width", "gtav_dit_workspace_bytes", "gtav_dit_plan_create", "gtav_dit_plan_destroy",
     "gtav_dit_conditioning", "gtav_dit_backbone", "gtav_dit_forward", "gtav_vae_create", "gtav_vae_destroy",
@@ -21,6 +22,8 @@ EXPORTS = [
     "gtav_sampler_cond_rows", "gtav_sampler_scratch_bytes", "gtav_sampler_create", "gtav_sampler_destroy",
     "gtav_sampler_run_frame", "gtav_noise_clamp",
 ]
+
+SAMPLER_GRAPH, SAMPLER_FRAME_CACHE = 1, 2      # gtav_sampler_flags
 
 vp = C.c_void_p
 
@@ -76,10 +79,14 @@ def load() -> C.CDLL:
     lib.gtav_abi_version.restype = i
     sig = {
         "gtav_gemm_bf16": [vp, i, vp, i, vp, i, i, i, i, i, vp, vp, i, vp, i, ip, i, i, vp],
+        "gtav_gemm_skinny_bf16": [vp, i, vp, i, vp, i, i, i, i, i, vp, vp, i, vp, i, ip, i, i, vp, vp, vp],
+        "gtav_dit_context": [vp, vp, i, ip, vp],
+        "gtav_dit_last_frame": [vp, vp, i, ip, vp, vp],
         "gtav_ln_modulate": [vp, vp, i, i, vp, i, i, i, ip, i, vp],
         "gtav_ln_affine": [vp, vp, i, i, fp, fp, vp],
         "gtav_attention_seq": [vp, vp, i, i, i, fp, i, vp],
         "gtav_attention_temporal": [vp, vp, i, i, i, i, fp, vp],
+        "gtav_attention_temporal_last": [vp, vp, i, i, i, i, fp, vp, vp],
         "gtav_ddim_update": [fp, vp, fp, i, i, fp, fp, ip, vp],
         "gtav_dit_create": [C.POINTER(DitConfig), C.POINTER(DitWeights), C.POINTER(vp)],
         "gtav_dit_destroy": [vp],
@@ -109,6 +116,8 @@ def load() -> C.CDLL:
     lib.gtav_dit_workspace_bytes.restype = sz
     lib.gtav_vae_workspace_bytes.argtypes = [vp, i]
     lib.gtav_vae_workspace_bytes.restype = sz
+    lib.gtav_gemm_skinny_workspace_bytes.argtypes = [i]
+    lib.gtav_gemm_skinny_workspace_bytes.restype = sz
     lib.gtav_sampler_scratch_bytes.argtypes = [i, i, i]
     lib.gtav_sampler_scratch_bytes.restype = sz
     _lib = lib

@@ -40,6 +40,8 @@ attn_seq_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads,
     static_assert(SEQ % KB == 0 && KB % 16 == 0 && SEQ % (WARPS * 16) == 0, "tiling");
     __shared__ __align__(16) bf16 sK[KB * SROW];
     __shared__ __align__(16) bf16 sV[KB * SROW];
+    pdl_trigger();
+    pdl_wait();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, tig = lane & 3;
@@ -78,6 +80,7 @@ attn_seq_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads,
     for (int kb0 = 0; kb0 < SEQ; kb0 += KB) {
         if (kb0 > 0) __syncthreads();                        // previous block fully consumed
         // ---- stage K (rotated) and V for keys [kb0, kb0+KB) ---------------------------------
+#pragma unroll 4
         for (int i = threadIdx.x; i < KB * 8; i += WARPS * 32) {
             const int r = i >> 3, c8 = (i & 7) * 8;
             const size_t goff = static_cast<size_t>(kb0 + r) * ld + c8;
@@ -182,14 +185,14 @@ int launch_attention_seq(const bf16* qkv, bf16* out, int groups, int seq, int he
                          cudaStream_t s) {
     if (groups <= 0) return 0;
     if (seq == 144 && rot_pairs == 32) {
-        attn_seq_kernel<144, 48, 9, 32><<<dim3(1, heads, groups), 9 * 32, 0, s>>>(qkv, out, heads, rot);
+        // all 144 keys of a head staged in one pass (one global round trip), queries split over 3 CTAs
+        GTAV_CUDA_OK(launch_k(attn_seq_kernel<144, 144, 3, 32>, dim3(3, heads, groups), dim3(3 * 32), 0, s, qkv, out, heads, rot));
     } else if (seq == 576 && rot_pairs == 16) {
-        attn_seq_kernel<576, 64, 4, 16><<<dim3(9, heads, groups), 4 * 32, 0, s>>>(qkv, out, heads, rot);
+        GTAV_CUDA_OK(launch_k(attn_seq_kernel<576, 64, 4, 16>, dim3(9, heads, groups), dim3(4 * 32), 0, s, qkv, out, heads, rot));
     } else {
         set_error("attention: unsupported (seq=%d, rot_pairs=%d); built for (144,32) and (576,16)", seq, rot_pairs);
         return -1;
     }
-    GTAV_CUDA_OK(cudaGetLastError());
     return 0;
 }
 

@@ -16,7 +16,9 @@ static constexpr int TA_WARPS = 8;
 template <int T>
 __global__ void __launch_bounds__(TA_WARPS * 32)
 attn_temporal_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int B, int P, int heads,
-                     const float2* __restrict__ rot) {
+                     const float2* __restrict__ rot, bf16* __restrict__ kv_cache) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const long wg = static_cast<long>(blockIdx.x) * TA_WARPS + (threadIdx.x >> 5);
     if (wg >= static_cast<long>(B) * P * heads) return;
@@ -40,6 +42,12 @@ attn_temporal_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int B
         q[t] = make_float2(bf16_round(qx.x * cs.x - qx.y * cs.y), bf16_round(qx.y * cs.x + qx.x * cs.y));
         k[t] = make_float2(bf16_round(kx.x * cs.x - kx.y * cs.y), bf16_round(kx.y * cs.x + kx.x * cs.y));
         v[t] = unpack_bf16x2(vu);
+        if (kv_cache != nullptr) {
+            // rotated K (already rounded to bf16) and V of every frame, row-for-row like qkv: [row][k | v][D]
+            bf16* c = kv_cache + row * (2 * D) + head * 64 + 2 * lane;
+            *reinterpret_cast<uint32_t*>(c) = pack_bf16x2(k[t].x, k[t].y);
+            *reinterpret_cast<uint32_t*>(c + D) = vu;
+        }
     }
 #pragma unroll
     for (int i = 0; i < T; ++i) {
@@ -69,14 +77,99 @@ attn_temporal_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int B
     }
 }
 
+// Last frame only: the query is the frame being denoised (window position TC = number of cached context
+// frames), keys/values are the TC cached context frames (rotated K and V written by attn_temporal_kernel
+// with kv_cache set) followed by the frame's own k/v.  Same arithmetic, in the same order, as row T-1 of
+// attn_temporal_kernel<TC+1>, so the cached step reproduces the dense step bit for bit.
+// qkv [B*P, 3D] (last-frame rows only), out [B*P, D], kv_cache [B*TC*P, 2D].
+template <int TC>
+__global__ void __launch_bounds__(TA_WARPS * 32)
+attn_temporal_last_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int B, int P, int heads,
+                          const float2* __restrict__ rot, const bf16* __restrict__ kv_cache) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const long wg = static_cast<long>(blockIdx.x) * TA_WARPS + (threadIdx.x >> 5);
+    if (wg >= static_cast<long>(B) * P * heads) return;
+    const int head = static_cast<int>(wg % heads);
+    const int pos = static_cast<int>((wg / heads) % P);
+    const int b = static_cast<int>(wg / (static_cast<long>(heads) * P));
+    const int D = heads * 64;
+
+    float2 k[TC + 1], v[TC + 1];
+#pragma unroll
+    for (int t = 0; t < TC; ++t) {
+        const size_t row = (static_cast<size_t>(b) * TC + t) * P + pos;
+        const bf16* c = kv_cache + row * (2 * D) + head * 64 + 2 * lane;
+        k[t] = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(c));
+        v[t] = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(c + D));
+    }
+    const size_t qrow = static_cast<size_t>(b) * P + pos;
+    const bf16* base = qkv + qrow * (3 * D) + head * 64 + 2 * lane;
+    const float2 cs = rot[TC * 32 + lane];
+    const float2 qx = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(base));
+    const float2 kx = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(base + D));
+    const float2 q = make_float2(bf16_round(qx.x * cs.x - qx.y * cs.y), bf16_round(qx.y * cs.x + qx.x * cs.y));
+    k[TC] = make_float2(bf16_round(kx.x * cs.x - kx.y * cs.y), bf16_round(kx.y * cs.x + kx.x * cs.y));
+    v[TC] = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(base + 2 * D));
+
+    float s[TC + 1];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j <= TC; ++j) {
+        s[j] = warp_sum(q.x * k[j].x + q.y * k[j].y) * 0.125f;
+        m = fmaxf(m, s[j]);
+    }
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j <= TC; ++j) {
+        s[j] = __expf(s[j] - m);
+        l += s[j];
+    }
+    const float inv = 1.0f / l;
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j <= TC; ++j) {
+        const float p = bf16_round(s[j] * inv);
+        acc.x += p * v[j].x;
+        acc.y += p * v[j].y;
+    }
+    *reinterpret_cast<uint32_t*>(out + qrow * D + head * 64 + 2 * lane) = pack_bf16x2(acc.x, acc.y);
+}
+
+int launch_attention_temporal_last(const bf16* qkv, bf16* out, int B, int ctx_frames, int positions, int heads,
+                                   const float2* rot, const bf16* kv_cache, cudaStream_t s) {
+    const long problems = static_cast<long>(B) * positions * heads;
+    if (problems <= 0) return 0;
+    if (ctx_frames > 0 && kv_cache == nullptr) {
+        set_error("temporal attention (last frame): missing K/V cache");
+        return -1;
+    }
+    const int grid = static_cast<int>((problems + TA_WARPS - 1) / TA_WARPS);
+#define GTAV_TL(TT)                                                                                          \
+    case TT:                                                                                                 \
+        GTAV_CUDA_OK(launch_k(attn_temporal_last_kernel<TT>, dim3(grid), dim3(TA_WARPS * 32), 0, s, qkv, out, B, positions, heads, \
+                              rot, kv_cache));                                                               \
+        break;
+    switch (ctx_frames) {
+        GTAV_TL(0) GTAV_TL(1) GTAV_TL(2) GTAV_TL(3) GTAV_TL(4) GTAV_TL(5) GTAV_TL(6) GTAV_TL(7)
+        default:
+            set_error("temporal attention (last frame): %d cached frames unsupported (0..7)", ctx_frames);
+            return -1;
+    }
+#undef GTAV_TL
+    return 0;
+}
+
 int launch_attention_temporal(const bf16* qkv, bf16* out, int B, int T, int positions, int heads, const float2* rot,
-                              cudaStream_t s) {
+                              bf16* kv_cache, cudaStream_t s) {
     const long problems = static_cast<long>(B) * positions * heads;
     if (problems <= 0) return 0;
     const int grid = static_cast<int>((problems + TA_WARPS - 1) / TA_WARPS);
 #define GTAV_TA(TT)                                                                                       \
     case TT:                                                                                              \
-        attn_temporal_kernel<TT><<<grid, TA_WARPS * 32, 0, s>>>(qkv, out, B, positions, heads, rot);       \
+        GTAV_CUDA_OK(launch_k(attn_temporal_kernel<TT>, dim3(grid), dim3(TA_WARPS * 32), 0, s, qkv, out, B, positions, heads, rot, \
+                              kv_cache));                                                                  \
         break;
     switch (T) {
         GTAV_TA(1) GTAV_TA(2) GTAV_TA(3) GTAV_TA(4) GTAV_TA(5) GTAV_TA(6) GTAV_TA(7) GTAV_TA(8)
@@ -85,7 +178,6 @@ int launch_attention_temporal(const bf16* qkv, bf16* out, int B, int T, int posi
             return -1;
     }
 #undef GTAV_TA
-    GTAV_CUDA_OK(cudaGetLastError());
     return 0;
 }
 

@@ -2,6 +2,8 @@
 // enqueues the kernel sequence that stands in for DiT.forward (reference model/dit.py:343-376) and
 // SpatioTemporalDiTBlock.forward (model/dit.py:200-225).  No allocation, no host sync: everything is
 // launched on the caller's stream so a whole step can be captured into a CUDA graph.
+#include <stdlib.h>
+
 #include <new>
 #include <vector>
 
@@ -20,13 +22,28 @@ struct gtav_dit_s {
     int out_feat;     // p*p*C
 };
 
+// GEMM launch descriptors for one row count (B * frames * tokens rows) over the plan's shared workspace.
+struct Shape {
+    int frames = 0, M = 0;
+    GemmOp g_patch, g_final;
+    std::vector<GemmOp> g_qkv, g_out, g_fc1, g_fc2;
+    // weight-streaming variants (last-frame shape only); sk[kind] says whether kind uses them
+    std::vector<SkinnyOp> s_qkv, s_out, s_fc1, s_fc2;
+    bool sk[4] = {false, false, false, false};
+};
+
+enum BackboneMode { MODE_FULL = 0, MODE_CONTEXT = 1, MODE_LAST = 2 };
+
 struct gtav_dit_plan_s {
     gtav_dit_t eng;
     int B, T, M, R;
     // workspace slices
     bf16 *xa, *h, *hn, *qkv, *att, *mlp, *yfin, *temb, *aemb, *h1, *cact, *mod;
-    GemmOp g_t0, g_t2, g_ada, g_patch, g_final;
-    std::vector<GemmOp> g_qkv, g_out, g_fc1, g_fc2;
+    bf16* kv_cache;          // [depth][B*(T-1)*tokens][2*hidden]: rotated K and V of the context frames per temporal layer
+    float* sk_ws;            // split-K partial sums of the weight-streaming GEMM
+    int* sk_counters;
+    GemmOp g_t0, g_t2, g_ada;
+    Shape full, ctx, last;   // all T frames / the T-1 context frames / the last frame only
 };
 
 namespace {
@@ -58,6 +75,11 @@ void carve(gtav_dit_plan_s* p, void* ws, size_t* total) {
     p->h1 = c.take(R * D);
     p->cact = c.take(R * D);
     p->mod = c.take(R * static_cast<size_t>(e->mod_width));
+    const size_t ctx_rows = static_cast<size_t>(p->B) * (p->T - 1) * e->tokens;
+    p->kv_cache = c.take(static_cast<size_t>(e->cfg.depth) * ctx_rows * 2 * D);
+    const int m_last = p->B * e->tokens;
+    p->sk_ws = reinterpret_cast<float*>(c.take(p->B <= 3 ? skinny_workspace_bytes(m_last) / sizeof(bf16) : 0));
+    p->sk_counters = reinterpret_cast<int*>(c.take(256));
     *total = c.off;
 }
 
@@ -68,12 +90,124 @@ GemmParams gp(bf16* out, int ldo, const void* bias, int M, int N, int K) {
     return p;
 }
 
+bool skinny_enabled() {
+    const char* e = getenv("GTAV_SKINNY");
+    return !(e != nullptr && e[0] == '0');
+}
+
+// Descriptors of the backbone GEMMs for `frames` frames per rollout.  allow_skinny: use the weight-streaming
+// kernel where the shape fits it (last-frame steps of at most 3 rollouts).
+int build_shape(gtav_dit_plan_s* p, Shape* sh, int frames, bool allow_skinny) {
+    const gtav_dit_s* h = p->eng;
+    const int D = h->cfg.hidden, S = h->tokens, W = h->mod_width;
+    const int M = p->B * frames * S;
+    const gtav_dit_weights& w = h->w;
+    sh->frames = frames;
+    sh->M = M;
+    int rc = 0;
+    rc |= gemm_prepare(&sh->g_patch, p->xa, 64, static_cast<const bf16*>(w.patch_w), 64, gp(p->h, D, w.patch_b, M, D, 64), EPI_BIAS);
+    const int nh = 2 * h->cfg.depth;
+    sh->g_qkv.resize(nh); sh->g_out.resize(nh); sh->g_fc1.resize(nh); sh->g_fc2.resize(nh);
+    const bool sk_ok = allow_skinny && skinny_enabled() && p->sk_ws != nullptr;
+    sh->sk[0] = sk_ok && skinny_pick_splits(M, 3 * D, D) > 0;
+    sh->sk[1] = sk_ok && skinny_pick_splits(M, D, D) > 0;
+    sh->sk[2] = sk_ok && skinny_pick_splits(M, 4 * D, D) > 0;
+    sh->sk[3] = sk_ok && skinny_pick_splits(M, D, 4 * D) > 0;
+    if (sh->sk[0]) sh->s_qkv.resize(nh);
+    if (sh->sk[1]) sh->s_out.resize(nh);
+    if (sh->sk[2]) sh->s_fc1.resize(nh);
+    if (sh->sk[3]) sh->s_fc2.resize(nh);
+    for (int i = 0; i < nh && rc == 0; ++i) {
+        const gtav_dit_half& hw = h->halves[i];
+        const bf16* modl = p->mod + static_cast<size_t>(i) * 6 * D;
+        const GemmParams pq = gp(p->qkv, 3 * D, nullptr, M, 3 * D, D);
+        GemmParams po = gp(p->h, D, hw.out_b, M, D, D);
+        po.res = p->h; po.ldr = D; po.gate = modl + 2 * D; po.gate_ld = W; po.rows_per_frame = S;
+        const GemmParams p1 = gp(p->mlp, 4 * D, hw.fc1_b, M, 4 * D, D);
+        GemmParams p2 = gp(p->h, D, hw.fc2_b, M, D, 4 * D);
+        p2.res = p->h; p2.ldr = D; p2.gate = modl + 5 * D; p2.gate_ld = W; p2.rows_per_frame = S;
+        if (sh->sk[0]) rc |= skinny_prepare(&sh->s_qkv[i], p->hn, D, static_cast<const bf16*>(hw.qkv_w), D, pq, EPI_STORE, p->sk_ws, p->sk_counters);
+        else rc |= gemm_prepare(&sh->g_qkv[i], p->hn, D, static_cast<const bf16*>(hw.qkv_w), D, pq, EPI_STORE);
+        if (sh->sk[1]) rc |= skinny_prepare(&sh->s_out[i], p->att, D, static_cast<const bf16*>(hw.out_w), D, po, EPI_BIAS_GATE_RES, p->sk_ws, p->sk_counters);
+        else rc |= gemm_prepare(&sh->g_out[i], p->att, D, static_cast<const bf16*>(hw.out_w), D, po, EPI_BIAS_GATE_RES);
+        if (sh->sk[2]) rc |= skinny_prepare(&sh->s_fc1[i], p->hn, D, static_cast<const bf16*>(hw.fc1_w), D, p1, EPI_BIAS_GELU_TANH, p->sk_ws, p->sk_counters);
+        else rc |= gemm_prepare(&sh->g_fc1[i], p->hn, D, static_cast<const bf16*>(hw.fc1_w), D, p1, EPI_BIAS_GELU_TANH);
+        if (sh->sk[3]) rc |= skinny_prepare(&sh->s_fc2[i], p->mlp, 4 * D, static_cast<const bf16*>(hw.fc2_w), 4 * D, p2, EPI_BIAS_GATE_RES, p->sk_ws, p->sk_counters);
+        else rc |= gemm_prepare(&sh->g_fc2[i], p->mlp, 4 * D, static_cast<const bf16*>(hw.fc2_w), 4 * D, p2, EPI_BIAS_GATE_RES);
+    }
+    rc |= gemm_prepare(&sh->g_final, p->hn, D, static_cast<const bf16*>(w.final_w), D, gp(p->yfin, 64, w.final_b, M, h->out_feat, D), EPI_BIAS);
+    return rc == 0 ? 0 : (rc < 0 ? rc : -1);
+}
+
+// The kernel sequence of DiT.forward's backbone on the rows of `sh`.  x: the [B, T, C, H, W] window; the frames
+// processed are first_frame .. first_frame + sh->frames - 1 of every rollout.  out == nullptr skips the final
+// layer (context pass: only the K/V caches are wanted).
+int run_backbone(gtav_dit_plan_s* p, const Shape* sh, int mode, const void* x, int x_is_bf16, int first_frame,
+                 const int* frame_row, void* out, cudaStream_t stream) {
+    const gtav_dit_s* e = p->eng;
+    const gtav_dit_config& c = e->cfg;
+    const int D = c.hidden, M = sh->M, S = e->tokens, W = e->mod_width, F = p->B * sh->frames;
+    const long frame_elems = static_cast<long>(c.in_channels) * c.grid_h * c.patch * c.grid_w * c.patch;
+    const char* x0 = static_cast<const char*>(x) + first_frame * frame_elems * (x_is_bf16 ? 2 : 4);
+    int rc = launch_patchify(x0, x_is_bf16, p->xa, 64, F, c.in_channels, c.grid_h * c.patch, c.grid_w * c.patch, c.patch,
+                             sh->frames, static_cast<long>(p->T) * frame_elems, stream);
+    if (rc) return rc;
+    if ((rc = gemm_run(&sh->g_patch, stream))) return rc;
+    const float2* rot_s = reinterpret_cast<const float2*>(e->w.rot_spatial);
+    const float2* rot_t = reinterpret_cast<const float2*>(e->w.rot_temporal);
+    const size_t cache_layer = static_cast<size_t>(p->B) * (p->T - 1) * S * 2 * D;
+    for (int i = 0; i < 2 * c.depth; ++i) {
+        const int off = i * 6 * D;          // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
+        if ((rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, off, off + D, frame_row, S, stream))) return rc;
+        if (sh->sk[0]) rc = skinny_run(&sh->s_qkv[i], stream);
+        else rc = gemm_run(&sh->g_qkv[i], stream);
+        if (rc) return rc;
+        if ((i & 1) == 0) {
+            rc = launch_attention_seq(p->qkv, p->att, F, S, c.heads, rot_s, 32, stream);
+        } else {
+            bf16* cache = p->kv_cache + static_cast<size_t>(i >> 1) * cache_layer;
+            if (mode == MODE_LAST) rc = launch_attention_temporal_last(p->qkv, p->att, p->B, p->T - 1, S, c.heads, rot_t, cache, stream);
+            else rc = launch_attention_temporal(p->qkv, p->att, p->B, sh->frames, S, c.heads, rot_t, mode == MODE_CONTEXT ? cache : nullptr, stream);
+        }
+        if (rc) return rc;
+        if (sh->sk[1]) {
+            SkinnyOp o = sh->s_out[i];
+            o.p.frame_row = frame_row;
+            rc = skinny_run(&o, stream);
+        } else {
+            GemmOp o = sh->g_out[i];
+            o.p.frame_row = frame_row;
+            rc = gemm_run(&o, stream);
+        }
+        if (rc) return rc;
+        if ((rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, off + 3 * D, off + 4 * D, frame_row, S, stream))) return rc;
+        if (sh->sk[2]) rc = skinny_run(&sh->s_fc1[i], stream);
+        else rc = gemm_run(&sh->g_fc1[i], stream);
+        if (rc) return rc;
+        if (sh->sk[3]) {
+            SkinnyOp o = sh->s_fc2[i];
+            o.p.frame_row = frame_row;
+            rc = skinny_run(&o, stream);
+        } else {
+            GemmOp o = sh->g_fc2[i];
+            o.p.frame_row = frame_row;
+            rc = gemm_run(&o, stream);
+        }
+        if (rc) return rc;
+    }
+    if (out == nullptr) return 0;
+    const int foff = 2 * c.depth * 6 * D;   // final layer: shift, scale
+    if ((rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, foff, foff + D, frame_row, S, stream))) return rc;
+    if ((rc = gemm_run(&sh->g_final, stream))) return rc;
+    return launch_dit_unpatchify(p->yfin, static_cast<bf16*>(out), F, c.in_channels, c.grid_h, c.grid_w, c.patch, stream);
+}
+
 }  // namespace
 
 extern "C" {
 
 const char* gtav_last_error(void) { return get_error(); }
-int gtav_abi_version(void) { return 1; }
+int gtav_abi_version(void) { return 2; }
 
 int gtav_dit_create(const gtav_dit_config* cfg, const gtav_dit_weights* w, gtav_dit_t* out) {
     if (!cfg || !w || !out) { set_error("dit_create: null argument"); return -1; }
@@ -132,7 +266,7 @@ int gtav_dit_plan_create(gtav_dit_t h, int B, int T, int cond_rows, void* worksp
         delete p;
         return -1;
     }
-    const int D = h->cfg.hidden, M = p->M, R = p->R, S = h->tokens, W = h->mod_width;
+    const int D = h->cfg.hidden, R = p->R, W = h->mod_width;
     const gtav_dit_weights& w = h->w;
     int rc = 0;
     // conditioning chain (rows = R)
@@ -143,23 +277,11 @@ int gtav_dit_plan_create(gtav_dit_t h, int B, int T, int cond_rows, void* worksp
         rc |= gemm_prepare(&p->g_t2, p->h1, D, static_cast<const bf16*>(w.t2_w), D, q, EPI_BIAS_RES_SILU);
     }
     rc |= gemm_prepare(&p->g_ada, p->cact, D, static_cast<const bf16*>(w.ada_w), D, gp(p->mod, W, w.ada_b, R, W, D), EPI_BIAS);
-    // backbone
-    rc |= gemm_prepare(&p->g_patch, p->xa, 64, static_cast<const bf16*>(w.patch_w), 64, gp(p->h, D, w.patch_b, M, D, 64), EPI_BIAS);
-    const int nh = 2 * h->cfg.depth;
-    p->g_qkv.resize(nh); p->g_out.resize(nh); p->g_fc1.resize(nh); p->g_fc2.resize(nh);
-    for (int i = 0; i < nh && rc == 0; ++i) {
-        const gtav_dit_half& hw = h->halves[i];
-        const bf16* modl = p->mod + static_cast<size_t>(i) * 6 * D;
-        rc |= gemm_prepare(&p->g_qkv[i], p->hn, D, static_cast<const bf16*>(hw.qkv_w), D, gp(p->qkv, 3 * D, nullptr, M, 3 * D, D), EPI_STORE);
-        GemmParams q = gp(p->h, D, hw.out_b, M, D, D);
-        q.res = p->h; q.ldr = D; q.gate = modl + 2 * D; q.gate_ld = W; q.rows_per_frame = S;
-        rc |= gemm_prepare(&p->g_out[i], p->att, D, static_cast<const bf16*>(hw.out_w), D, q, EPI_BIAS_GATE_RES);
-        rc |= gemm_prepare(&p->g_fc1[i], p->hn, D, static_cast<const bf16*>(hw.fc1_w), D, gp(p->mlp, 4 * D, hw.fc1_b, M, 4 * D, D), EPI_BIAS_GELU_TANH);
-        GemmParams r = gp(p->h, D, hw.fc2_b, M, D, 4 * D);
-        r.res = p->h; r.ldr = D; r.gate = modl + 5 * D; r.gate_ld = W; r.rows_per_frame = S;
-        rc |= gemm_prepare(&p->g_fc2[i], p->mlp, 4 * D, static_cast<const bf16*>(hw.fc2_w), 4 * D, r, EPI_BIAS_GATE_RES);
-    }
-    rc |= gemm_prepare(&p->g_final, p->hn, D, static_cast<const bf16*>(w.final_w), D, gp(p->yfin, 64, w.final_b, M, h->out_feat, D), EPI_BIAS);
+    // backbone: one set of descriptors per row count
+    if (rc == 0) rc = build_shape(p, &p->full, T, false);
+    if (rc == 0 && T >= 2) rc = build_shape(p, &p->ctx, T - 1, false);
+    if (rc == 0) rc = build_shape(p, &p->last, 1, true);
+    if (rc == 0 && cudaMemset(p->sk_counters, 0, 512) != cudaSuccess) { set_error("dit_plan_create: clearing the split-K counters failed"); rc = -2; }
     if (rc) { delete p; return rc < 0 ? rc : -1; }
     *out = p;
     return 0;
@@ -186,33 +308,19 @@ int gtav_dit_conditioning(gtav_dit_plan_t p, const int64_t* t, const float* acti
 int gtav_dit_backbone(gtav_dit_plan_t p, const void* x, int x_is_bf16, const int* frame_row, void* out,
                       gtav_stream_t stream) {
     if (!p || !x || !out) { set_error("dit_backbone: null argument"); return -1; }
-    const gtav_dit_s* e = p->eng;
-    const gtav_dit_config& c = e->cfg;
-    const int D = c.hidden, M = p->M, S = e->tokens, W = e->mod_width, F = p->B * p->T;
-    int rc = launch_patchify(x, x_is_bf16, p->xa, 64, F, c.in_channels, c.grid_h * c.patch, c.grid_w * c.patch, c.patch, 1.f, stream);
-    if (rc) return rc;
-    if ((rc = gemm_run(&p->g_patch, stream))) return rc;
-    const float2* rot_s = reinterpret_cast<const float2*>(e->w.rot_spatial);
-    const float2* rot_t = reinterpret_cast<const float2*>(e->w.rot_temporal);
-    for (int i = 0; i < 2 * c.depth; ++i) {
-        const int off = i * 6 * D;          // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
-        GemmOp g_out = p->g_out[i], g_fc2 = p->g_fc2[i];
-        g_out.p.frame_row = frame_row;
-        g_fc2.p.frame_row = frame_row;
-        if ((rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, off, off + D, frame_row, S, stream))) return rc;
-        if ((rc = gemm_run(&p->g_qkv[i], stream))) return rc;
-        if ((i & 1) == 0) rc = launch_attention_seq(p->qkv, p->att, F, S, c.heads, rot_s, 32, stream);
-        else rc = launch_attention_temporal(p->qkv, p->att, p->B, p->T, S, c.heads, rot_t, stream);
-        if (rc) return rc;
-        if ((rc = gemm_run(&g_out, stream))) return rc;
-        if ((rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, off + 3 * D, off + 4 * D, frame_row, S, stream))) return rc;
-        if ((rc = gemm_run(&p->g_fc1[i], stream))) return rc;
-        if ((rc = gemm_run(&g_fc2, stream))) return rc;
-    }
-    const int foff = 2 * c.depth * 6 * D;   // final layer: shift, scale
-    if ((rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, foff, foff + D, frame_row, S, stream))) return rc;
-    if ((rc = gemm_run(&p->g_final, stream))) return rc;
-    return launch_dit_unpatchify(p->yfin, static_cast<bf16*>(out), F, c.in_channels, c.grid_h, c.grid_w, c.patch, stream);
+    return run_backbone(p, &p->full, MODE_FULL, x, x_is_bf16, 0, frame_row, out, stream);
+}
+
+int gtav_dit_context(gtav_dit_plan_t p, const void* x, int x_is_bf16, const int* frame_row, gtav_stream_t stream) {
+    if (!p || !x) { set_error("dit_context: null argument"); return -1; }
+    if (p->T < 2) return 0;                  // a one-frame window has no context
+    return run_backbone(p, &p->ctx, MODE_CONTEXT, x, x_is_bf16, 0, frame_row, nullptr, stream);
+}
+
+int gtav_dit_last_frame(gtav_dit_plan_t p, const void* x, int x_is_bf16, const int* frame_row, void* out,
+                        gtav_stream_t stream) {
+    if (!p || !x || !out) { set_error("dit_last_frame: null argument"); return -1; }
+    return run_backbone(p, &p->last, MODE_LAST, x, x_is_bf16, p->T - 1, frame_row, out, stream);
 }
 
 int gtav_dit_forward(gtav_dit_plan_t p, const void* x, int x_is_bf16, const int64_t* t, const float* actions,
@@ -242,6 +350,25 @@ int gtav_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, in
     return gemm_run(&op, stream);
 }
 
+size_t gtav_gemm_skinny_workspace_bytes(int M) { return skinny_workspace_bytes(M); }
+
+int gtav_gemm_skinny_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
+                          int epilogue, const void* bias, const void* res, int ldr, const void* gate, int gate_ld,
+                          const int* frame_row, int rows_per_frame, int splits, void* workspace, int* counters,
+                          gtav_stream_t stream) {
+    if (!workspace || !counters) { set_error("gemm_skinny: workspace and counters are required"); return -1; }
+    GemmParams p{};
+    p.out = static_cast<bf16*>(out); p.ldo = ldo; p.bias = static_cast<const bf16*>(bias);
+    p.res = static_cast<const bf16*>(res); p.ldr = ldr; p.gate = static_cast<const bf16*>(gate); p.gate_ld = gate_ld;
+    p.frame_row = frame_row; p.rows_per_frame = rows_per_frame > 0 ? rows_per_frame : 1;
+    p.M = M; p.N = N; p.K = K;
+    SkinnyOp op;
+    int rc = skinny_prepare(&op, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), ldw, p, epilogue,
+                            static_cast<float*>(workspace), counters, splits);
+    if (rc) return rc;
+    return skinny_run(&op, stream);
+}
+
 int gtav_ln_modulate(const void* x, void* out, int M, int D, const void* mod, int mod_ld, int shift_off, int scale_off,
                      const int* frame_row, int rows_per_frame, gtav_stream_t stream) {
     return launch_ln_modulate(static_cast<const bf16*>(x), static_cast<bf16*>(out), M, D, static_cast<const bf16*>(mod),
@@ -258,7 +385,12 @@ int gtav_attention_seq(const void* qkv, void* out, int groups, int seq, int head
 int gtav_attention_temporal(const void* qkv, void* out, int B, int T, int positions, int heads, const float* rot,
                             gtav_stream_t stream) {
     return launch_attention_temporal(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), B, T, positions, heads,
-                                     reinterpret_cast<const float2*>(rot), stream);
+                                     reinterpret_cast<const float2*>(rot), nullptr, stream);
+}
+int gtav_attention_temporal_last(const void* qkv, void* out, int B, int ctx_frames, int positions, int heads,
+                                 const float* rot, const void* kv_cache, gtav_stream_t stream) {
+    return launch_attention_temporal_last(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), B, ctx_frames, positions,
+                                          heads, reinterpret_cast<const float2*>(rot), static_cast<const bf16*>(kv_cache), stream);
 }
 int gtav_ddim_update(const float* x, const void* v_bf16, float* out, int F, int n, const float* abar_t,
                      const float* abar_next, const int* final_flag, gtav_stream_t stream) {

@@ -13,6 +13,8 @@ namespace gtav {
 __global__ void cond_prep_kernel(const int64_t* __restrict__ t, const float* __restrict__ actions, int act_dim,
                                  const float* __restrict__ freqs, const bf16* __restrict__ Wa,
                                  const bf16* __restrict__ ba, bf16* __restrict__ temb, bf16* __restrict__ aemb, int D) {
+    pdl_trigger();
+    pdl_wait();
     const int r = blockIdx.x;
     const float tv = static_cast<float>(t[r]);
     for (int i = threadIdx.x; i < 128; i += blockDim.x) {
@@ -39,8 +41,7 @@ int launch_cond_prep(const int64_t* t, const float* actions, int act_dim, int R,
         set_error("cond_prep: action dimension %d > 64", act_dim);
         return -1;
     }
-    cond_prep_kernel<<<R, 256, 0, s>>>(t, actions, act_dim, freqs, Wa, ba, temb, aemb, D);
-    GTAV_CUDA_OK(cudaGetLastError());
+    GTAV_CUDA_OK(launch_k(cond_prep_kernel, dim3(R), dim3(256), 0, s, t, actions, act_dim, freqs, Wa, ba, temb, aemb, D));
     return 0;
 }
 
@@ -51,7 +52,9 @@ int launch_cond_prep(const int64_t* t, const float* actions, int act_dim, int R,
 // ------------------------------------------------------------------------------------------
 template <typename Tin>
 __global__ void patchify_kernel(const Tin* __restrict__ x, bf16* __restrict__ out, int ldo, int F, int C, int H, int W,
-                                int p, long total) {
+                                int p, long total, int frames_per_group, long group_stride) {
+    pdl_trigger();
+    pdl_wait();
     const int gw = W / p, gh = H / p, pp = p * p, K = C * pp;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -62,14 +65,16 @@ __global__ void patchify_kernel(const Tin* __restrict__ x, bf16* __restrict__ ou
             const int wx = static_cast<int>(row % gw), hy = static_cast<int>((row / gw) % gh);
             const long f = row / (static_cast<long>(gw) * gh);
             const int c = k / pp, ph = (k % pp) / p, pw = k % p;
-            v = static_cast<float>(x[((f * C + c) * H + hy * p + ph) * W + wx * p + pw]);
+            // frame f = (group g, j): groups of frames_per_group contiguous frames, group_stride elements apart
+            const long fbase = (f / frames_per_group) * group_stride + (f % frames_per_group) * static_cast<long>(C) * H * W;
+            v = static_cast<float>(x[fbase + (static_cast<long>(c) * H + hy * p + ph) * W + wx * p + pw]);
         }
         out[i] = __float2bfloat16_rn(v);
     }
 }
 
-int launch_patchify(const void* x, int x_is_bf16, bf16* out, int ldo, int F, int C, int H, int W, int p, float,
-                    cudaStream_t s) {
+int launch_patchify(const void* x, int x_is_bf16, bf16* out, int ldo, int F, int C, int H, int W, int p,
+                    int frames_per_group, long group_stride, cudaStream_t s) {
     if (H % p || W % p || C * p * p > ldo) {
         set_error("patchify: bad geometry C=%d H=%d W=%d p=%d ldo=%d", C, H, W, p, ldo);
         return -1;
@@ -77,11 +82,13 @@ int launch_patchify(const void* x, int x_is_bf16, bf16* out, int ldo, int F, int
     const long total = static_cast<long>(F) * (H / p) * (W / p) * ldo;
     if (total <= 0) return 0;
     const int grid = static_cast<int>(min(static_cast<long>(148 * 16), (total + 255) / 256));
+    if (frames_per_group <= 0) { frames_per_group = F > 0 ? F : 1; group_stride = 0; }
     if (x_is_bf16)
-        patchify_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), out, ldo, F, C, H, W, p, total);
+        GTAV_CUDA_OK(launch_k(patchify_kernel<bf16>, dim3(grid), dim3(256), 0, s, static_cast<const bf16*>(x), out, ldo, F, C, H, W, p,
+                              total, frames_per_group, group_stride));
     else
-        patchify_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), out, ldo, F, C, H, W, p, total);
-    GTAV_CUDA_OK(cudaGetLastError());
+        GTAV_CUDA_OK(launch_k(patchify_kernel<float>, dim3(grid), dim3(256), 0, s, static_cast<const float*>(x), out, ldo, F, C, H, W, p,
+                              total, frames_per_group, group_stride));
     return 0;
 }
 
@@ -90,6 +97,8 @@ int launch_patchify(const void* x, int x_is_bf16, bf16* out, int ldo, int F, int
 // ------------------------------------------------------------------------------------------
 __global__ void dit_unpatchify_kernel(const bf16* __restrict__ y, bf16* __restrict__ out, int C, int gh, int gw, int p,
                                       long total) {
+    pdl_trigger();
+    pdl_wait();
     const int H = gh * p, W = gw * p, ldy = p * p * C;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -105,8 +114,7 @@ int launch_dit_unpatchify(const bf16* y, bf16* out, int F, int C, int gh, int gw
     const long total = static_cast<long>(F) * C * gh * p * gw * p;
     if (total <= 0) return 0;
     const int grid = static_cast<int>(min(static_cast<long>(148 * 16), (total + 255) / 256));
-    dit_unpatchify_kernel<<<grid, 256, 0, s>>>(y, out, C, gh, gw, p, total);
-    GTAV_CUDA_OK(cudaGetLastError());
+    GTAV_CUDA_OK(launch_k(dit_unpatchify_kernel, dim3(grid), dim3(256), 0, s, y, out, C, gh, gw, p, total));
     return 0;
 }
 
@@ -117,6 +125,8 @@ int launch_dit_unpatchify(const bf16* y, bf16* out, int F, int C, int gh, int gw
 template <bool TO_U8>
 __global__ void vae_unpatchify_kernel(const bf16* __restrict__ y, void* __restrict__ out, int sh, int sw, int p,
                                       long total_pixels) {
+    pdl_trigger();
+    pdl_wait();
     const int H = sh * p, W = sw * p, pp = p * p, ldy = 3 * pp;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total_pixels;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -143,9 +153,8 @@ int launch_vae_unpatchify(const bf16* y, void* out, int to_u8, int F, int sh, in
     const long total = static_cast<long>(F) * sh * p * sw * p;
     if (total <= 0) return 0;
     const int grid = static_cast<int>(min(static_cast<long>(148 * 32), (total + 255) / 256));
-    if (to_u8) vae_unpatchify_kernel<true><<<grid, 256, 0, s>>>(y, out, sh, sw, p, total);
-    else vae_unpatchify_kernel<false><<<grid, 256, 0, s>>>(y, out, sh, sw, p, total);
-    GTAV_CUDA_OK(cudaGetLastError());
+    if (to_u8) GTAV_CUDA_OK(launch_k(vae_unpatchify_kernel<true>, dim3(grid), dim3(256), 0, s, y, out, sh, sw, p, total));
+    else GTAV_CUDA_OK(launch_k(vae_unpatchify_kernel<false>, dim3(grid), dim3(256), 0, s, y, out, sh, sw, p, total));
     return 0;
 }
 
@@ -154,6 +163,8 @@ int launch_vae_unpatchify(const bf16* y, void* out, int to_u8, int F, int sh, in
 // ------------------------------------------------------------------------------------------
 __global__ void cast_pad_kernel(const float* __restrict__ z, bf16* __restrict__ out, long rows, int C, int ldo,
                                 float divisor) {
+    pdl_trigger();
+    pdl_wait();
     const long total = rows * ldo;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -167,13 +178,14 @@ int launch_cast_pad(const float* z, bf16* out, int rows, int C, int ldo, float d
     const long total = static_cast<long>(rows) * ldo;
     if (total <= 0) return 0;
     const int grid = static_cast<int>(min(static_cast<long>(148 * 16), (total + 255) / 256));
-    cast_pad_kernel<<<grid, 256, 0, s>>>(z, out, rows, C, ldo, divisor);
-    GTAV_CUDA_OK(cudaGetLastError());
+    GTAV_CUDA_OK(launch_k(cast_pad_kernel, dim3(grid), dim3(256), 0, s, z, out, static_cast<long>(rows), C, ldo, divisor));
     return 0;
 }
 
 __global__ void take_mean_kernel(const bf16* __restrict__ moments, int ldm, float* __restrict__ out, long rows, int C,
                                  float scale, int round_bf16) {
+    pdl_trigger();
+    pdl_wait();
     const long total = rows * C;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -187,8 +199,7 @@ int launch_take_mean(const bf16* moments, int ldm, float* out, int rows, int C, 
     const long total = static_cast<long>(rows) * C;
     if (total <= 0) return 0;
     const int grid = static_cast<int>(min(static_cast<long>(148 * 16), (total + 255) / 256));
-    take_mean_kernel<<<grid, 256, 0, s>>>(moments, ldm, out, rows, C, scale, round_bf16);
-    GTAV_CUDA_OK(cudaGetLastError());
+    GTAV_CUDA_OK(launch_k(take_mean_kernel, dim3(grid), dim3(256), 0, s, moments, ldm, out, static_cast<long>(rows), C, scale, round_bf16));
     return 0;
 }
 
@@ -200,6 +211,8 @@ int launch_take_mean(const bf16* moments, int ldm, float* out, int rows, int C, 
 __global__ void ddim_kernel(const float* __restrict__ x, long x_stride, const bf16* __restrict__ v, long v_stride,
                             float* __restrict__ out, long out_stride, int n, const float* __restrict__ abar_t,
                             const float* __restrict__ abar_next, const int* __restrict__ final_flag) {
+    pdl_trigger();
+    pdl_wait();
     const int f = blockIdx.y;
     const float a = abar_t[f], an = abar_next[f];
     const float c_x = sqrtf(a), c_v = sqrtf(__fsub_rn(1.0f, a));
@@ -222,9 +235,8 @@ __global__ void ddim_kernel(const float* __restrict__ x, long x_stride, const bf
 int launch_ddim(const float* x, long x_stride, const bf16* v, long v_stride, float* out, long out_stride, int F, int n,
                 const float* abar_t, const float* abar_next, const int* final_flag, cudaStream_t s) {
     if (F <= 0 || n <= 0) return 0;
-    ddim_kernel<<<dim3((n + 255) / 256, F), 256, 0, s>>>(x, x_stride, v, v_stride, out, out_stride, n, abar_t, abar_next,
-                                                        final_flag);
-    GTAV_CUDA_OK(cudaGetLastError());
+    GTAV_CUDA_OK(launch_k(ddim_kernel, dim3((n + 255) / 256, F), dim3(256), 0, s, x, x_stride, v, v_stride, out, out_stride, n, abar_t,
+                          abar_next, final_flag));
     return 0;
 }
 
@@ -238,8 +250,10 @@ namespace gtav {
 // last frame of rollout b at step k -> B*(T-1) + b*(steps+1) + k.
 // ------------------------------------------------------------------------------------------
 __global__ void step_prep_kernel(int* counter, const int* __restrict__ levels, const float* __restrict__ abar, int B,
-                                 int T, int steps, int* __restrict__ frame_row, float* __restrict__ abar_t,
-                                 float* __restrict__ abar_next, int* __restrict__ final_flag) {
+                                 int T, int steps, int* __restrict__ frame_row, int* __restrict__ last_row,
+                                 float* __restrict__ abar_t, float* __restrict__ abar_next, int* __restrict__ final_flag) {
+    pdl_trigger();
+    pdl_wait();
     const int k = *counter;
     __syncthreads();
     for (int f = threadIdx.x; f < B * T; f += blockDim.x) {
@@ -250,6 +264,7 @@ __global__ void step_prep_kernel(int* counter, const int* __restrict__ levels, c
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         abar_t[b] = at;
         abar_next[b] = an;
+        last_row[b] = B * (T - 1) + b * (steps + 1) + k;       // the same row, for the last-frame-only backbone
     }
     if (threadIdx.x == 0) {
         *final_flag = k <= 0 ? 1 : 0;
@@ -258,22 +273,25 @@ __global__ void step_prep_kernel(int* counter, const int* __restrict__ levels, c
 }
 
 int launch_step_prep(int* counter, const int* levels, const float* abar, int B, int T, int steps, int* frame_row,
-                     float* abar_t, float* abar_next, int* final_flag, cudaStream_t s) {
-    step_prep_kernel<<<1, 256, 0, s>>>(counter, levels, abar, B, T, steps, frame_row, abar_t, abar_next, final_flag);
-    GTAV_CUDA_OK(cudaGetLastError());
+                     int* last_row, float* abar_t, float* abar_next, int* final_flag, cudaStream_t s) {
+    GTAV_CUDA_OK(launch_k(step_prep_kernel, dim3(1), dim3(256), 0, s, counter, levels, abar, B, T, steps, frame_row, last_row, abar_t,
+                          abar_next, final_flag));
     return 0;
 }
 
-__global__ void set_int_kernel(int* dst, int value) { *dst = value; }
+__global__ void set_int_kernel(int* dst, int value) {
+    pdl_trigger();
+    pdl_wait(); *dst = value; }
 
 int launch_set_int(int* dst, int value, cudaStream_t s) {
-    set_int_kernel<<<1, 1, 0, s>>>(dst, value);
-    GTAV_CUDA_OK(cudaGetLastError());
+    GTAV_CUDA_OK(launch_k(set_int_kernel, dim3(1), dim3(1), 0, s, dst, value));
     return 0;
 }
 
 __global__ void noise_clamp_kernel(const float* __restrict__ noise, float* __restrict__ x, long x_stride, int n,
                                    float amax) {
+    pdl_trigger();
+    pdl_wait();
     const int f = blockIdx.y;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         x[f * x_stride + i] = fminf(fmaxf(noise[static_cast<long>(f) * n + i], -amax), amax);
@@ -281,8 +299,7 @@ __global__ void noise_clamp_kernel(const float* __restrict__ noise, float* __res
 
 int launch_noise_clamp(const float* noise, float* x, long x_stride, int F, int n, float amax, cudaStream_t s) {
     if (F <= 0 || n <= 0) return 0;
-    noise_clamp_kernel<<<dim3((n + 255) / 256, F), 256, 0, s>>>(noise, x, x_stride, n, amax);
-    GTAV_CUDA_OK(cudaGetLastError());
+    GTAV_CUDA_OK(launch_k(noise_clamp_kernel, dim3((n + 255) / 256, F), dim3(256), 0, s, noise, x, x_stride, n, amax));
     return 0;
 }
 

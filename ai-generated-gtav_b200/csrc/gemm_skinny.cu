@@ -1,0 +1,293 @@
+// Weight-streaming bf16 GEMM for the last-frame DiT step: out[T,N] = epilogue(A[T,K] @ W[N,K]^T) with very
+// few token rows (T = 144 per rollout, at most 3 rollouts per call) and large weights.
+//
+// Same reference ops as gemm_sm100.cu (to_qkv / to_out / Mlp.fc1 / Mlp.fc2 of reference
+// model/attention.py:27-28,86-87 and model/dit.py:171-198) - this is the shape they take once the
+// context frames' K/V are cached and only the frame being denoised is recomputed (M = 144*B).
+// At that size the op is bound by streaming W from HBM and A from L2, not by the tensor pipe, so the
+// kernel is organised around getting all SMs to pull bytes at once:
+//   * operands are swapped: the UMMA "M" side is a block of 128 weight rows, the "N" side one
+//     144-token frame tile (a legal UMMA N, no padding), accumulator D[128 x 144] fp32 in TMEM;
+//   * K is split over S CTAs per weight-row block so that (N/128)*S ~ the SM count; every CTA
+//     loads its whole operand slab with ONE TMA instruction per operand (3-D box spanning all its
+//     64-wide K chunks: measured on B200, a TMA instruction costs ~0.4 us of issue time per warp
+//     whatever its size, so few large boxes from two producer warps beat many 16 KB ones);
+//   * the W slab is requested before griddepcontrol.wait (weights do not depend on the previous
+//     kernel), so HBM latency hides behind the previous kernel's tail;
+//   * partial accumulators go to an fp32 workspace (L2), the S CTAs of a row block meet on a
+//     counter, and each reduces + runs the fused epilogue for its 1/S share of the tokens, summing
+//     the partials in split order (deterministic).
+// Warp roles (256 threads): 0 = W producer, 1 = A producer, 2 = TMEM allocator + MMA issuer,
+// 4-7 = epilogue (one TMEM lane quadrant each).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gtav {
+
+static constexpr int SK_THREADS = 256;
+static constexpr int SK_NT = 144;                  // tokens per tile (one frame)
+static constexpr int SK_W_CHUNK = 128 * 128;       // bytes: 128 weight rows x 64 bf16
+static constexpr int SK_A_CHUNK = SK_NT * 128;     // bytes: 144 tokens x 64 bf16
+static constexpr int SK_SMEM_BUDGET = 200 * 1024;
+
+struct SkinnyParams {
+    GemmParams g;
+    int splits, chunks, tiles;
+    float* ws;
+    int* counters;
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// One output element: column n (this thread's weight row), token `tok`, fp32 pre-bias value `acc`.
+template <int EPI>
+__device__ __forceinline__ void skinny_store(const GemmParams& g, int tok, int n, float acc, float bias_n) {
+    float y = acc;
+    if (EPI != EPI_STORE) y += bias_n;
+    y = bf16_round(y);                                           // the Linear's own bf16 output
+    if (EPI == EPI_BIAS_GELU_TANH) {
+        y = gelu_tanh_f(y);
+    } else if (EPI == EPI_BIAS_GATE_RES) {
+        int f = tok / g.rows_per_frame;
+        if (g.frame_row != nullptr) f = g.frame_row[f];
+        const float gt = __bfloat162float(g.gate[static_cast<size_t>(f) * g.gate_ld + n]);
+        const float r = __bfloat162float(g.res[static_cast<size_t>(tok) * g.ldr + n]);
+        y = r + bf16_round(gt * y);
+    }
+    g.out[static_cast<size_t>(tok) * g.ldo + n] = __float2bfloat16_rn(y);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(SK_THREADS, 1)
+gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const SkinnyParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int chunks = p.chunks, tiles = p.tiles, S = p.splits;
+    uint8_t* sW = smem;
+    uint8_t* sA = smem + chunks * SK_W_CHUNK;
+    uint64_t* bar_w = reinterpret_cast<uint64_t*>(sA + tiles * chunks * SK_A_CHUNK);
+    uint64_t* bar_a = bar_w + 1;                   // [tiles] (<= 3)
+    uint64_t* bar_acc = bar_w + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rb = blockIdx.x / S, split = blockIdx.x - rb * S;
+    const int kc0 = split * chunks;
+    const uint32_t tmem_cols = tiles * SK_NT <= 256 ? 256u : 512u;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmW);
+        tma_prefetch_desc(&tmA);
+        mbar_init(bar_w, 1);
+        for (int t = 0; t < tiles; ++t) mbar_init(&bar_a[t], 1);
+        mbar_init(bar_acc, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, tmem_cols);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar_w, chunks * SK_W_CHUNK);
+            tma_load_3d(sW, &tmW, bar_w, 0, rb * 128, kc0);
+        }
+        pdl_wait();
+    } else if (warp == 1) {
+        pdl_wait();
+        if (lane == 0) {
+            for (int t = 0; t < tiles; ++t) {
+                mbar_arrive_expect_tx(&bar_a[t], chunks * SK_A_CHUNK);
+                tma_load_3d(sA + t * chunks * SK_A_CHUNK, &tmA, &bar_a[t], 0, t * SK_NT, kc0);
+            }
+        }
+    } else if (warp == 2) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, SK_NT);
+            mbar_wait(bar_w, 0);
+            for (int t = 0; t < tiles; ++t) {
+                mbar_wait(&bar_a[t], 0);
+                tcgen05_fence_after();
+                for (int ch = 0; ch < chunks; ++ch) {
+                    const uint64_t dw = umma_desc_sw128(smem_u32(sW + ch * SK_W_CHUNK));
+                    const uint64_t da = umma_desc_sw128(smem_u32(sA + (t * chunks + ch) * SK_A_CHUNK));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_ss(tmem_base + t * SK_NT, dw + 2 * k, da + 2 * k, idesc, (ch | k) != 0 ? 1u : 0u);
+                }
+            }
+            umma_commit(bar_acc);
+        }
+        pdl_wait();
+    } else if (warp >= 4) {
+        pdl_wait();
+        const GemmParams& g = p.g;
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int n = rb * 128 + row;
+        const int total = tiles * SK_NT;
+        float bias_n = 0.f;
+        if (EPI != EPI_STORE) bias_n = __bfloat162float(g.bias[n]);
+        mbar_wait(bar_acc, 0);
+        tcgen05_fence_after();
+        const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        if (S == 1) {
+#pragma unroll 1
+            for (int c = 0; c < total; c += 16) {
+                uint32_t v[16];
+                tmem_ld_32x16(tlane + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) skinny_store<EPI>(g, c + i, n, __uint_as_float(v[i]), bias_n);
+            }
+        } else {
+            float* mine = p.ws + static_cast<size_t>(blockIdx.x) * total * 128;
+#pragma unroll 1
+            for (int c = 0; c < total; c += 16) {
+                uint32_t v[16];
+                tmem_ld_32x16(tlane + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) __stcg(mine + static_cast<size_t>(c + i) * 128 + row, __uint_as_float(v[i]));
+            }
+            __threadfence();
+            epi_bar_sync();
+            int* arrive = p.counters + 2 * rb;
+            if (threadIdx.x == 128) {
+                atomicAdd(arrive, 1);
+                uint32_t spins = 0;
+                while (ld_acquire_gpu(arrive) < S) {
+                    __nanosleep(64);
+                    if (++spins > (1u << 24)) {
+                        printf("gtav: split-K rendezvous timed out (block %d)\n", blockIdx.x);
+                        __trap();
+                    }
+                }
+            }
+            epi_bar_sync();
+            const int lo = split * total / S, hi = (split + 1) * total / S;
+            const float* part = p.ws + static_cast<size_t>(rb) * S * total * 128 + row;
+#pragma unroll 1
+            for (int tok = lo; tok < hi; ++tok) {
+                float acc = 0.f;
+                for (int s2 = 0; s2 < S; ++s2) acc += __ldcg(part + (static_cast<size_t>(s2) * total + tok) * 128);
+                skinny_store<EPI>(g, tok, n, acc, bias_n);
+            }
+            epi_bar_sync();
+            if (threadIdx.x == 128) {
+                const int old = atomicAdd(arrive + 1, 1);
+                if (old == S - 1) {                       // everyone of this row block is past the rendezvous
+                    arrive[1] = 0;
+                    __threadfence();
+                    atomicExch(arrive, 0);
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------ host
+bool skinny_supported(int M, int N, int K, int epi) {
+    if (M <= 0 || M % SK_NT != 0 || M / SK_NT > 3) return false;
+    if (N % 128 != 0 || K % 64 != 0) return false;
+    return epi == EPI_STORE || epi == EPI_BIAS || epi == EPI_BIAS_GELU_TANH || epi == EPI_BIAS_GATE_RES;
+}
+
+// Largest K split S (dividing the 64-wide chunk count) such that the per-CTA operand slab fits shared memory and
+// all (N/128)*S CTAs are co-resident (they rendezvous on a counter).  0 = this shape does not fit the kernel.
+int skinny_pick_splits(int M, int N, int K) {
+    if (M <= 0 || M % SK_NT != 0 || M / SK_NT > 3 || N % 128 != 0 || K % 64 != 0 || N / 128 > 64) return 0;
+    int sms = 148;
+    {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            sms = n;
+    }
+    if (sms > 160) sms = 160;
+    const int tiles = M / SK_NT, rbs = N / 128, kchunks = K / 64;
+    const int per_chunk = SK_W_CHUNK + tiles * SK_A_CHUNK;
+    int best = 0;
+    for (int s = 1; s <= kchunks; ++s) {
+        if (kchunks % s) continue;
+        if ((kchunks / s) * per_chunk > SK_SMEM_BUDGET) continue;
+        if (rbs * s > sms) break;
+        best = s;
+    }
+    return best;
+}
+
+size_t skinny_workspace_bytes(int M) { return static_cast<size_t>(160) * M * 128 * sizeof(float); }
+
+int skinny_prepare(SkinnyOp* op, const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi, float* ws,
+                   int* counters, int splits_override) {
+    if (!skinny_supported(p.M, p.N, p.K, epi)) {
+        set_error("skinny gemm: unsupported shape/epilogue M=%d N=%d K=%d epi=%d", p.M, p.N, p.K, epi);
+        return -1;
+    }
+    if (epi == EPI_BIAS_GATE_RES && (p.gate == nullptr || p.res == nullptr || p.rows_per_frame != SK_NT)) {
+        set_error("skinny gemm: gated-residual epilogue needs gate, residual and rows_per_frame == %d", SK_NT);
+        return -1;
+    }
+    const int tiles = p.M / SK_NT, rbs = p.N / 128, kchunks = p.K / 64;
+    const int per_chunk = SK_W_CHUNK + tiles * SK_A_CHUNK;
+    int S = splits_override > 0 ? splits_override : skinny_pick_splits(p.M, p.N, p.K);
+    if (S <= 0 || kchunks % S || (kchunks / S) * per_chunk > SK_SMEM_BUDGET || rbs * S > 160 || rbs > 64) {
+        set_error("skinny gemm: no valid K split for M=%d N=%d K=%d (S=%d)", p.M, p.N, p.K, S);
+        return -1;
+    }
+    op->p = p;
+    op->epi = epi;
+    op->splits = S;
+    op->chunks = kchunks / S;
+    op->tiles = tiles;
+    op->ws = ws;
+    op->counters = counters;
+    int rc = make_tmap_3d(&op->tmW, W, p.N, p.K, ldw, 128, op->chunks);
+    if (rc) return rc;
+    return make_tmap_3d(&op->tmA, A, p.M, p.K, lda, SK_NT, op->chunks);
+}
+
+template <int EPI>
+static int skinny_launch(const SkinnyOp* op, cudaStream_t stream) {
+    static bool configured = false;
+    auto kern = gemm_skinny_kernel<EPI>;
+    if (!configured) {
+        GTAV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BUDGET + 2048));
+        configured = true;
+    }
+    SkinnyParams sp;
+    sp.g = op->p; sp.splits = op->splits; sp.chunks = op->chunks; sp.tiles = op->tiles; sp.ws = op->ws; sp.counters = op->counters;
+    // At least half of the SM's shared memory, so that exactly one CTA of this kernel fits on an SM: the CTAs of a
+    // row block wait for each other, and a second CTA on the same SM could block in tcgen05.alloc behind a waiting one.
+    size_t smem = static_cast<size_t>(op->chunks) * (SK_W_CHUNK + op->tiles * SK_A_CHUNK) + 64 + 1024;
+    if (smem < 120 * 1024) smem = 120 * 1024;
+    GTAV_CUDA_OK(launch_k(kern, dim3((op->p.N / 128) * op->splits), dim3(SK_THREADS), smem, stream, op->tmW, op->tmA, sp));
+    return 0;
+}
+
+int skinny_run(const SkinnyOp* op, cudaStream_t stream) {
+    switch (op->epi) {
+        case EPI_STORE: return skinny_launch<EPI_STORE>(op, stream);
+        case EPI_BIAS: return skinny_launch<EPI_BIAS>(op, stream);
+        case EPI_BIAS_GELU_TANH: return skinny_launch<EPI_BIAS_GELU_TANH>(op, stream);
+        case EPI_BIAS_GATE_RES: return skinny_launch<EPI_BIAS_GATE_RES>(op, stream);
+    }
+    set_error("skinny gemm: unknown epilogue %d", op->epi);
+    return -1;
+}
+
+}  // namespace gtav

@@ -13,6 +13,7 @@
 // the epilogue.  Out-of-range rows / columns / K are zero-filled by TMA and masked in the epilogue.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -149,10 +150,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();                                // the next kernel may start its own set-up now
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
+            // W tiles are weights (never written by the kernel before us): start streaming them before
+            // waiting for the previous kernel, so HBM latency overlaps its tail.  A waits.
+            const int pre = num_kb < STAGES ? num_kb : STAGES;
+            for (int kb = 0; kb < pre; ++kb) {
+                mbar_arrive_expect_tx(&full_bar[kb], L::A_BYTES + L::B_BYTES);
+                tma_load_2d(sB + kb * L::B_BYTES, &tmB, &full_bar[kb], kb * BK, n_blk * BN);
+            }
+            pdl_wait();
+            for (int kb = 0; kb < pre; ++kb) tma_load_2d(sA + kb * L::A_BYTES, &tmA, &full_bar[kb], kb * BK, m_blk * BM);
+            for (int kb = pre; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
@@ -161,6 +172,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tma_load_2d(sB + s * L::B_BYTES, &tmB, &full_bar[s], kb * BK, n_blk * BN);
             }
         }
+        pdl_wait();
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
@@ -180,7 +192,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             umma_commit(accum_bar);               // accumulator complete
         }
+        pdl_wait();
     } else {
+        pdl_wait();                               // bias / gate / residual may come from the previous kernel
         const int q = warp & 3;                   // TMEM lane quadrant this warp may read
         const int row = m_blk * BM + q * 32 + lane;
         const bf16* gate_row = nullptr;
@@ -252,6 +266,33 @@ static int make_tmap(CUtensorMap* out, const bf16* ptr, uint64_t rows, uint64_t 
     return 0;
 }
 
+int make_tmap_3d(CUtensorMap* out, const bf16* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                 uint32_t box_chunks) {
+    EncodeTiledFn enc = encode_fn();
+    if (enc == nullptr) {
+        set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+        return -3;
+    }
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld % 8) != 0 || (cols % BK) != 0 || box_rows > 256 || box_chunks > 256) {
+        set_error("GEMM operand (3-D view) must be 16-byte aligned, ld %% 8 == 0, K %% 64 == 0 (ptr=%p ld=%llu K=%llu)", ptr,
+                  (unsigned long long)ld, (unsigned long long)cols);
+        return -1;
+    }
+    cuuint64_t gdim[3] = {static_cast<cuuint64_t>(BK), rows, cols / BK};
+    cuuint64_t gstride[2] = {ld * sizeof(bf16), BK * sizeof(bf16)};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(BK), box_rows, box_chunks};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d (rows=%llu cols=%llu ld=%llu box=%ux%u)", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_chunks);
+        return -3;
+    }
+    return 0;
+}
+
 static int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -314,8 +355,7 @@ static int launch_one(const GemmOp* op, cudaStream_t stream) {
         configured = true;
     }
     dim3 grid((op->p.N + BN - 1) / BN, (op->p.M + BM - 1) / BM, 1);
-    kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(op->tmA, op->tmB, op->p);
-    GTAV_CUDA_OK(cudaGetLastError());
+    GTAV_CUDA_OK(launch_k(kern, grid, dim3(GEMM_THREADS), L::TOTAL, stream, op->tmA, op->tmB, op->p));
     return 0;
 }
 
@@ -346,6 +386,15 @@ int gemm_run(const GemmOp* op, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------
 // error text
 // ------------------------------------------------------------------------------------------
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("GTAV_PDL");
+        on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
+}
+
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
     va_list ap;

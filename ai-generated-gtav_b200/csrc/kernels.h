@@ -22,6 +22,24 @@ const char* get_error();
         }                                                                                      \
     } while (0)
 
+// Launch with the programmatic-dependent-launch attribute (see common.cuh: pdl_wait / pdl_trigger).
+// GTAV_PDL=0 in the environment turns the attribute off (plain stream order) for A/B measurements.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------- GEMM (gemm_sm100.cu)
 enum Epilogue : int {
     EPI_STORE = 0,           // out = bf16(acc)
@@ -58,6 +76,29 @@ int gemm_prepare(GemmOp* op, const bf16* A, int lda, const bf16* W, int ldw, con
                  int bn_override = 0);
 int gemm_run(const GemmOp* op, cudaStream_t stream);
 
+// [rows, cols] bf16 row-major (leading dimension ld) viewed as [64 | rows | cols/64]: boxes of
+// box_rows x (box_chunks * 64) land in shared memory as box_chunks consecutive 128-byte-swizzled
+// (box_rows x 64) tiles - one TMA instruction per multi-chunk slab.
+int make_tmap_3d(CUtensorMap* out, const bf16* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                 uint32_t box_chunks);
+
+// ---------------------------------------------------------------- weight-streaming GEMM (gemm_skinny.cu)
+// Same contract as the GEMM above for M = 144 * {1,2,3} token rows (last-frame DiT step): operands swapped
+// (weights on the UMMA M side), K split over CTAs with an in-kernel deterministic reduction.
+struct SkinnyOp {
+    CUtensorMap tmW, tmA;
+    GemmParams p;
+    int epi, splits, chunks, tiles;
+    float* ws;        // fp32 partial-sum workspace, skinny_workspace_bytes(M)
+    int* counters;    // 128 zero-initialised ints (rendezvous counters, self-resetting)
+};
+bool skinny_supported(int M, int N, int K, int epi);
+int skinny_pick_splits(int M, int N, int K);
+size_t skinny_workspace_bytes(int M);
+int skinny_prepare(SkinnyOp* op, const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi, float* ws,
+                   int* counters, int splits_override = 0);
+int skinny_run(const SkinnyOp* op, cudaStream_t stream);
+
 // ---------------------------------------------------------------- row kernels (norm_mod.cu)
 // out = bf16( LN(x) * bf16(1 + bf16(scale + 1e-6)) + shift ), LN without affine, eps 1e-6.
 // shift/scale of row r live at mod + frame_row[r / rows_per_frame] * mod_ld + {shift_off, scale_off}.
@@ -73,17 +114,24 @@ int launch_ln_affine(const bf16* x, bf16* out, int M, int D, const float* w, con
 int launch_attention_seq(const bf16* qkv, bf16* out, int groups, int seq, int heads, const float2* rot, int rot_pairs,
                          cudaStream_t s);
 // Causal attention over the T frames of each (b, spatial position, head); rows ordered (b, t, pos).
-// rot: float2 [T][32] window-relative angles.
+// rot: float2 [T][32] window-relative angles.  kv_cache (optional) [B*T*positions, 2*H*64]: receives the rotated
+// K and the V of every row, for later last-frame-only steps.
 int launch_attention_temporal(const bf16* qkv, bf16* out, int B, int T, int positions, int heads, const float2* rot,
-                              cudaStream_t s);
+                              bf16* kv_cache, cudaStream_t s);
+// The same attention for the LAST frame of a (ctx_frames + 1)-frame window only: qkv / out hold the last-frame
+// rows [B*positions, ...], the context frames' K/V come from kv_cache [B*ctx_frames*positions, 2*H*64].
+int launch_attention_temporal_last(const bf16* qkv, bf16* out, int B, int ctx_frames, int positions, int heads,
+                                   const float2* rot, const bf16* kv_cache, cudaStream_t s);
 
 // ---------------------------------------------------------------- conditioning / patches / sampler (elementwise.cu)
 // temb[r, 0:128] = cos(t_r f), temb[r,128:256] = sin(t_r f) (bf16); aemb[r,:] = bf16(act_r @ Wa^T + ba) if actions.
 int launch_cond_prep(const int64_t* t, const float* actions, int act_dim, int R, const float* freqs, const bf16* Wa,
                      const bf16* ba, bf16* temb, bf16* aemb, int D, cudaStream_t s);
 // x [F, C, H, W] (fp32 or bf16) -> patches [F*(H/p)*(W/p), ldo] bf16, k = c*p*p + ph*p + pw, zero padded to ldo.
-int launch_patchify(const void* x, int x_is_bf16, bf16* out, int ldo, int F, int C, int H, int W, int p, float scale,
-                    cudaStream_t s);
+// Frames come in groups of frames_per_group contiguous frames whose starts are group_stride elements apart
+// (a sub-window of every rollout of a [B, T, C, H, W] tensor); frames_per_group <= 0 = all F frames contiguous.
+int launch_patchify(const void* x, int x_is_bf16, bf16* out, int ldo, int F, int C, int H, int W, int p,
+                    int frames_per_group, long group_stride, cudaStream_t s);
 // DiT un-patchify: y [F*gh*gw, p*p*C] -> v [F, C, gh*p, gw*p] bf16, feature = ph*(p*C) + pw*C + c.
 int launch_dit_unpatchify(const bf16* y, bf16* out, int F, int C, int gh, int gw, int p, cudaStream_t s);
 // VAE un-patchify: y [F*sh*sw, 3*p*p] -> img [F,3,sh*p,sw*p] bf16 (feature = c*p*p + ph*p + pw), or, with
@@ -99,9 +147,10 @@ int launch_take_mean(const bf16* moments, int ldm, float* out, int rows, int C, 
 int launch_ddim(const float* x, long x_stride, const bf16* v, long v_stride, float* out, long out_stride, int F, int n,
                 const float* abar_t, const float* abar_next, const int* final_flag, cudaStream_t s);
 // Sampler bookkeeping for one DDIM step, read from / written to device memory so a captured graph can be
-// replayed: k = *counter; frame_row, abar_t, abar_next, final_flag for step k; *counter = k - 1.
+// replayed: k = *counter; frame_row [B*T], last_row [B] (conditioning row of each rollout's last frame), abar_t,
+// abar_next, final_flag for step k; *counter = k - 1.
 int launch_step_prep(int* counter, const int* levels, const float* abar, int B, int T, int steps, int* frame_row,
-                     float* abar_t, float* abar_next, int* final_flag, cudaStream_t s);
+                     int* last_row, float* abar_t, float* abar_next, int* final_flag, cudaStream_t s);
 int launch_set_int(int* dst, int value, cudaStream_t s);
 // x[f*stride + i] = clamp(noise[f*n + i], -amax, amax)  (generate.py:201-203)
 int launch_noise_clamp(const float* noise, float* x, long x_stride, int F, int n, float amax, cudaStream_t s);

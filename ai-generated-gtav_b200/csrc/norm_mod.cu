@@ -18,6 +18,8 @@ ln_rows_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int M, const 
                int shift_off, int scale_off, const int* __restrict__ frame_row, int rows_per_frame,
                const float* __restrict__ w, const float* __restrict__ b) {
     constexpr int D = CHUNKS * 256;
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -94,9 +96,9 @@ int launch_ln_modulate(const bf16* x, bf16* out, int M, int D, const bf16* mod, 
         return -1;
     }
     if (M <= 0) return 0;
-    ln_rows_kernel<4, false><<<(M + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, s>>>(
-        x, out, M, mod, mod_ld, shift_off, scale_off, frame_row, rows_per_frame, nullptr, nullptr);
-    GTAV_CUDA_OK(cudaGetLastError());
+    GTAV_CUDA_OK(launch_k(ln_rows_kernel<4, false>, dim3((M + LN_WARPS - 1) / LN_WARPS), dim3(LN_WARPS * 32), 0, s, x, out, M, mod,
+                          mod_ld, shift_off, scale_off, frame_row, rows_per_frame, static_cast<const float*>(nullptr),
+                          static_cast<const float*>(nullptr)));
     return 0;
 }
 
@@ -106,9 +108,8 @@ int launch_ln_affine(const bf16* x, bf16* out, int M, int D, const float* w, con
         return -1;
     }
     if (M <= 0) return 0;
-    ln_rows_kernel<4, true><<<(M + LN_WARPS - 1) / LN_WARPS, LN_WARPS * 32, 0, s>>>(x, out, M, nullptr, 0, 0, 0, nullptr, 1,
-                                                                                  w, b);
-    GTAV_CUDA_OK(cudaGetLastError());
+    GTAV_CUDA_OK(launch_k(ln_rows_kernel<4, true>, dim3((M + LN_WARPS - 1) / LN_WARPS), dim3(LN_WARPS * 32), 0, s, x, out, M,
+                          static_cast<const bf16*>(nullptr), 0, 0, 0, static_cast<const int*>(nullptr), 1, w, b));
     return 0;
 }
 

@@ -161,7 +161,7 @@ int gtav_vae_encode(gtav_vae_plan_t p, const void* img, int img_is_bf16, float* 
     if (!p || !img || !mean_out) { set_error("vae_encode: null argument"); return -1; }
     const gtav_vae_s* e = p->eng;
     const gtav_vae_config& c = e->cfg;
-    int rc = launch_patchify(img, img_is_bf16, p->pa, e->patch_ld, p->N, 3, c.seq_h * c.patch, c.seq_w * c.patch, c.patch, 1.f, stream);
+    int rc = launch_patchify(img, img_is_bf16, p->pa, e->patch_ld, p->N, 3, c.seq_h * c.patch, c.seq_w * c.patch, c.patch, 0, 0L, stream);
     if (rc) return rc;
     if ((rc = gemm_run(&p->g_patch, stream))) return rc;
     for (size_t i = 0; i < e->enc.size(); ++i)

@@ -250,6 +250,40 @@ class DiT(nn.Module):
         return out
 
 
+    @torch.no_grad()
+    def forward_last_frame(self, x, t, external_cond=None):
+        """v-prediction of the LAST frame of the window only, computed the way the sampler's frame cache does it:
+        context pass over frames 0..T-2 (stores every temporal layer's K/V), then the last frame alone against that
+        cache.  Equals forward(x, t, external_cond)[:, -1:] (frames before the last cannot see it: per-frame
+        spatial attention, causal temporal attention - reference model/attention.py:62,127)."""
+        N.require_cuda(x, "x")
+        B, T, Cc, H, W = x.shape
+        if T > self.max_frames:
+            raise RuntimeError(f"window of {T} frames exceeds max_frames={self.max_frames}")
+        self._pack()
+        lib = N.load()
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        x = x.contiguous()
+        dev = x.device
+        t = t.to(device=dev, dtype=torch.long).reshape(B * T).contiguous()
+        act = None
+        if torch.is_tensor(external_cond):
+            act = external_cond.to(device=dev, dtype=torch.float32).reshape(B * T, self.external_cond_dim).contiguous()
+        rows = torch.arange(B * T, dtype=torch.int32, device=dev).reshape(B, T)
+        ctx_rows, last_rows = rows[:, :-1].contiguous(), rows[:, -1].contiguous()
+        out = torch.empty((B, 1, Cc, H, W), dtype=torch.bfloat16, device=dev)
+        is_bf16 = int(x.dtype == torch.bfloat16)
+        with torch.cuda.device(dev):
+            plan = self._plan(B, T)
+            s = N.current_stream()
+            N.check(lib.gtav_dit_conditioning(plan, t.data_ptr(), N.ptr(act), s), "gtav_dit_conditioning")
+            N.check(lib.gtav_dit_context(plan, x.data_ptr(), is_bf16, ctx_rows.data_ptr(), s), "gtav_dit_context")
+            N.check(lib.gtav_dit_last_frame(plan, x.data_ptr(), is_bf16, last_rows.data_ptr(), out.data_ptr(), s),
+                    "gtav_dit_last_frame")
+        return out
+
+
 def DiT_S_2():
     return DiT(input_h=18, input_w=32, patch_size=2, hidden_size=1024, depth=16, num_heads=16, max_frames=5)
 

@@ -127,23 +127,43 @@ def synthetic_prompt(B, n):
     return col.view(1, n, 3, 1, 1).expand(B, n, 3, 360, 640).contiguous()
 
 
-def launches_per_rollout(wl, depth=16, enc=6, dec=12):
+def launches_per_rollout(wl, algorithm, depth=16, enc=6, dec=12):
     """Kernels of OURS launched per rollout batch (mirrors dit_engine.cu / vae_engine.cu / sampler.cu)."""
-    backbone = 2 + 2 * depth * 7 + 3
-    step = 1 + backbone + 1
+    backbone = 2 + 2 * depth * 7 + 3                           # patchify, patch GEMM, 7 per half, final LN/GEMM/unpatchify
+    step = 1 + backbone + 1                                    # step_prep, backbone (window or last frame), ddim
     gen = wl["total"] - wl["n_prompt"]
-    per_frame = 1 + 1 + 4 + (wl["steps"] + 1) * step          # clamp, set_int, conditioning(4), steps
+    context = (2 + 2 * depth * 7) if algorithm == "cached" else 0
+    per_frame = 1 + 1 + 4 + context + (wl["steps"] + 1) * step  # clamp, set_int, conditioning(4), context pass, steps
     vae_enc = 2 + enc * 7 + 3
     vae_dec = 2 + dec * 7 + 3
     return gen * per_frame + vae_enc + vae_dec * ((wl["B"] * wl["total"] + 31) // 32)
 
 
+def _hot_weights(dit):
+    """Packed bf16 weights in _pack order: per half qkv_w, out_w, out_b, fc1_w, fc1_b, fc2_w, fc2_b."""
+    dit._pack()
+    keep = dit._engine[1]
+    return [keep[i * 7:(i + 1) * 7] for i in range(2 * dit.depth)]
+
+
+def _time_passes(one_pass, reps=10):
+    for _ in range(3):
+        one_pass()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        one_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
 def gemm_roofline(dit, B, pk):
-    """Time the four hot GEMM shapes of a DiT step with CUDA events through the C ABI, cycling through the
-    16 blocks' own weight matrices so weights come from HBM (1.2 GB >> 126 MB L2) as in the real step."""
+    """Tensor roofline of the tiled tcgen05 GEMM (the dense-window step's dominant kernel): the four hot GEMM
+    shapes of a DiT step with CUDA events through the C ABI, cycling through the 16 blocks' own weight matrices so
+    weights come from HBM (1.2 GB >> 126 MB L2) as in the real step."""
     import gtav_b200._native as N
     lib = N.load()
-    dit._pack()
     M = B * 5 * 144
     dev = torch.device("cuda")
     D = 1024
@@ -151,9 +171,7 @@ def gemm_roofline(dit, B, pk):
                 o1=torch.empty((M, D), device=dev, dtype=torch.bfloat16), o3=torch.empty((M, 3 * D), device=dev, dtype=torch.bfloat16),
                 o4=torch.empty((M, 4 * D), device=dev, dtype=torch.bfloat16))
     bias = torch.zeros(4 * D, device=dev, dtype=torch.bfloat16)
-    keep = dit._engine[1]
-    # packed bf16 weights in _pack order: per half qkv_w, out_w, out_b, fc1_w, fc1_b, fc2_w, fc2_b
-    halves = [keep[i * 7:(i + 1) * 7] for i in range(2 * dit.depth)]
+    halves = _hot_weights(dit)
     s = N.current_stream()
 
     def run(a, w, out, n, k, epi):
@@ -166,20 +184,52 @@ def gemm_roofline(dit, B, pk):
             run(bufs["a1"], h[1], bufs["o1"], D, D, N.EPI_BIAS)
             run(bufs["a1"], h[3], bufs["o4"], 4 * D, D, N.EPI_BIAS_GELU_TANH)
             run(bufs["a4"], h[5], bufs["o1"], D, 4 * D, N.EPI_BIAS)
-    for _ in range(3):
-        one_pass()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
-    e0.record()
-    for _ in range(reps):
-        one_pass()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps                     # GEMM time of one DiT step (128 launches)
+    ms = _time_passes(one_pass)                         # GEMM time of one DiT step (128 launches)
     tf = DIT_GEMM_GFLOP * B / ms                        # GFLOP / ms = TFLOP/s
     return dict(bound="tensor", achieved=round(tf, 1), peak=pk["tf"], unit="TFLOP/s", frac=round(tf / pk["tf"], 4),
-                traffic=None, kernel="gemm_bf16_kernel (tcgen05, 128 launches per DiT step)",
+                traffic=None, kernel="gemm_bf16_kernel (tcgen05, 128 launches per dense DiT step)",
                 gemm_ms_per_dit_step=round(ms, 4), peak_source=f"{pk['src']} sustained bf16")
+
+
+def skinny_roofline(dit, B, pk):
+    """HBM roofline of the weight-streaming GEMM (the last-frame step's dominant kernel): algorithmic bytes per
+    launch = the weight matrix (read once) + the token operand and result, / the average launch time, over the 128
+    launches of one step on the blocks' own weights (805 MB per pass >> L2, so every launch streams from HBM)."""
+    import gtav_b200._native as N
+    lib = N.load()
+    M = B * 144
+    if B > 3:
+        return None
+    dev = torch.device("cuda")
+    D = 1024
+    a1 = torch.randn((M, D), device=dev).to(torch.bfloat16)
+    a4 = torch.randn((M, 4 * D), device=dev).to(torch.bfloat16)
+    o1 = torch.empty((M, D), device=dev, dtype=torch.bfloat16)
+    o3 = torch.empty((M, 3 * D), device=dev, dtype=torch.bfloat16)
+    o4 = torch.empty((M, 4 * D), device=dev, dtype=torch.bfloat16)
+    bias = torch.zeros(4 * D, device=dev, dtype=torch.bfloat16)
+    ws = torch.empty(lib.gtav_gemm_skinny_workspace_bytes(M), dtype=torch.uint8, device=dev)
+    counters = torch.zeros(128, dtype=torch.int32, device=dev)
+    halves = _hot_weights(dit)
+    s = N.current_stream()
+    shapes = [(0, a1, o3, 3 * D, D, N.EPI_STORE), (1, a1, o1, D, D, N.EPI_BIAS), (3, a1, o4, 4 * D, D, N.EPI_BIAS_GELU_TANH),
+              (5, a4, o1, D, 4 * D, N.EPI_BIAS)]
+    if B > 1:
+        return None
+
+    def one_pass():
+        for h in halves:
+            for wi, a, out, n, k, epi in shapes:
+                N.check(lib.gtav_gemm_skinny_bf16(a.data_ptr(), k, h[wi].data_ptr(), k, out.data_ptr(), n, M, n, k, epi, bias.data_ptr(),
+                                                  None, 0, None, 0, None, 144, 0, ws.data_ptr(), counters.data_ptr(), s), "gemm_skinny")
+    ms = _time_passes(one_pass)
+    per_half = sum(2 * (n * k + M * k + M * n) for _, _, _, n, k, _ in shapes)          # bf16 bytes: W + A + out
+    gb = len(halves) * per_half / 1e9
+    gbs = gb / (ms / 1e3)
+    return dict(bound="hbm", achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s", frac=round(gbs / pk["hbm"], 4), traffic=None,
+                kernel="gemm_skinny_kernel (tcgen05 weight-streaming GEMM, 128 launches per last-frame DiT step)",
+                algorithmic_mb_per_launch=round(gb * 1e3 / (4 * len(halves)), 3), us_per_launch=round(ms * 1e3 / (4 * len(halves)), 3),
+                gemm_ms_per_last_frame_step=round(ms, 4), peak_source=f"{pk['src']} HBM copy bandwidth")
 
 
 def cpu_baseline(wl, max_seconds=25.0):
@@ -239,7 +289,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--algorithm", default="cached", choices=["cached", "dense"],
+                    help="cached: context pass per frame + last-frame-only steps (default, same results); "
+                         "dense: every step recomputes the whole window like the reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-algorithm comparison leg")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -263,7 +317,8 @@ def main():
     from gtav_b200.sampler import Sampler
     pk = peaks()
     dit, vae = build_models(dev)
-    sampler = Sampler(dit, vae, noise_steps=wl["steps"])
+    cached = args.algorithm == "cached"
+    sampler = Sampler(dit, vae, noise_steps=wl["steps"], frame_cache=cached)
     B, total, n_prompt = wl["B"], wl["total"], wl["n_prompt"]
     gen = total - n_prompt
     prompt_host = synthetic_prompt(B, n_prompt).pin_memory()
@@ -311,38 +366,66 @@ def main():
     rollout_e2e()
     ms_e2e = timed(rollout_e2e, args.steps)
 
-    # ms per DiT step: one frame's 101 graph replays, device-timed
-    lat = sampler.encode_prompt(prompt_dev)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    sampler.sample_latents(lat, actions, n_prompt + 2, generator=gen_rng)
-    e1.record()
-    torch.cuda.synchronize()
-    ms_dit_step = e0.elapsed_time(e1) / (2 * (wl["steps"] + 1))
+    # ms per DiT step: two generated frames (context pass, if cached, + steps+1 steps each), device-timed
+    def time_frames(smp, n_frames=2):
+        lat = smp.encode_prompt(prompt_dev)
+        smp.sample_latents(lat, actions, n_prompt + 1, generator=gen_rng)          # capture / warm
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        smp.sample_latents(lat, actions, n_prompt + n_frames, generator=gen_rng)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (n_frames * (wl["steps"] + 1))
+    ms_dit_step = time_frames(sampler)
 
     if rank == 0:
-        roof = gemm_roofline(dit, B, pk)
         frames_total = world * B * gen * args.steps
         value = frames_total / (ms_total / 1000.0)
         e2e_v = frames_total / (ms_e2e / 1000.0)
-        step_tf = DIT_STEP_GFLOP * B / ms_dit_step
+        T = 5
+        step_dense_gf = DIT_STEP_GFLOP * B
+        if cached:
+            # executed FLOPs per generated frame: one (T-1)-frame context pass + (steps+1) last-frame steps
+            last_gf = (116.411 + 1.359 + 0.009437 * T) * B
+            ctx_gf = (116.411 + 1.359) * (T - 1) * B + 0.009437 * (T - 1) ** 2 * B
+            exec_gf_per_step = (ctx_gf + (wl["steps"] + 1) * last_gf) / (wl["steps"] + 1)
+            roof = skinny_roofline(dit, B, pk) or gemm_roofline(dit, B, pk)
+            algo = ("frame cache: per generated frame one context pass over the T-1 context frames stores every temporal "
+                    "layer's K/V, then each of the steps+1 DDIM steps recomputes only the frame being denoised (144*B rows) "
+                    "against it - same arithmetic per row as the dense window (bit-identical with the tiled GEMM, "
+                    "tests/test_model_gpu.py), 4.8x fewer executed FLOPs")
+        else:
+            exec_gf_per_step = step_dense_gf
+            roof = gemm_roofline(dit, B, pk)
+            algo = "dense (every step recomputes the whole 5-frame window, like the reference)"
         line = dict(metric=METRIC, value=round(value, 3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=round(ms_total / args.steps, 2), higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="bf16", data="synthetic",
                     config=dict(workload=wl["desc"], rollouts_per_gpu=B, frames=total, prompt_frames=n_prompt,
                                 noise_steps=wl["steps"], dit_evals_per_rollout=gen * (wl["steps"] + 1),
                                 weights="random-init DiT-S/2 (607.9M) + ViT-L-20 VAE (229.2M), adaLN non-zero",
-                                l2="inputs larger than L2: 1.2 GB of bf16 weights streamed per DiT step (L2 126 MB)",
-                                algorithm="dense (every step recomputes the whole 5-frame window, like the reference)"),
+                                l2="inputs larger than L2: 0.8-1.2 GB of bf16 weights streamed per DiT step (L2 126 MB)",
+                                algorithm=algo),
                     ms_per_dit_step=round(ms_dit_step, 4),
-                    step_roofline=dict(bound="tensor", achieved=round(step_tf, 1), peak=pk["tf"], unit="TFLOP/s",
-                                       frac=round(step_tf / pk["tf"], 4),
-                                       note="whole DiT step: 589.09 GFLOP x B / measured ms per graph-replayed step"),
+                    step_roofline=dict(bound="tensor", executed_tflops=round(exec_gf_per_step / ms_dit_step, 1),
+                                       reference_equivalent_tflops=round(step_dense_gf / ms_dit_step, 1), peak=pk["tf"],
+                                       unit="TFLOP/s", frac_executed=round(exec_gf_per_step / ms_dit_step / pk["tf"], 4),
+                                       note="executed = FLOPs this algorithm runs per DDIM step / measured ms per step; "
+                                            "reference-equivalent = the dense window's 589.09 GFLOP x B / the same time"),
                     roofline=roof,
                     e2e=dict(value=round(e2e_v, 3), unit=UNIT, h2d_bytes_per_step=prompt_host.numel() * 4,
                              d2h_bytes_per_step=out_host.numel()),
-                    gpu_launches=launches_per_rollout(wl) * args.steps, clocks=clocks)
+                    gpu_launches=launches_per_rollout(wl, args.algorithm) * args.steps, clocks=clocks)
+        if cached and not args.no_dense:
+            # the dense algorithm on the same box, for the record: ms per dense step and the tiled GEMM's tensor roofline
+            dense = Sampler(dit, vae, noise_steps=wl["steps"], frame_cache=False)
+            ms_dense = time_frames(dense, n_frames=1)
+            dense.close()
+            line["dense"] = dict(ms_per_dit_step=round(ms_dense, 4), frames_per_s=round(B * 1000.0 / (ms_dense * (wl["steps"] + 1)), 3),
+                                 step_tflops=round(step_dense_gf / ms_dense, 1), frac=round(step_dense_gf / ms_dense / pk["tf"], 4),
+                                 gemm_roofline=gemm_roofline(dit, B, pk),
+                                 note="every step recomputes the whole window; DiT steps only (no VAE), 1 generated frame timed")
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl)
         print(json.dumps(line), flush=True)

@@ -56,6 +56,16 @@ int gtav_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, in
                    int epilogue, const void* bias, const void* res, int ldr, const void* gate, int gate_ld,
                    const int* frame_row, int rows_per_frame, int bn, gtav_stream_t stream);
 
+/* The same contract on the weight-streaming kernel used for last-frame steps: M = 144, 288 or 432 rows, N a
+ * multiple of 128, K of 64; epilogues STORE / BIAS / BIAS_GELU_TANH / BIAS_GATE_RES (rows_per_frame must be 144).
+ * workspace: fp32 scratch of gtav_gemm_skinny_workspace_bytes(M) bytes; counters: 128 ints, zero before the first
+ * call (they reset themselves).  splits = 0 lets the library pick the K split. */
+size_t gtav_gemm_skinny_workspace_bytes(int M);
+int gtav_gemm_skinny_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
+                          int epilogue, const void* bias, const void* res, int ldr, const void* gate, int gate_ld,
+                          const int* frame_row, int rows_per_frame, int splits, void* workspace, int* counters,
+                          gtav_stream_t stream);
+
 /* modulate(LayerNorm(x), shift, scale) of dit.py:19-27 -> bf16 [M, D]; D = 1024. */
 int gtav_ln_modulate(const void* x, void* out, int M, int D, const void* mod, int mod_ld, int shift_off, int scale_off,
                      const int* frame_row, int rows_per_frame, gtav_stream_t stream);
@@ -68,6 +78,11 @@ int gtav_attention_seq(const void* qkv, void* out, int groups, int seq, int head
 /* Causal attention over frames with fused rotary (attention.py:41-66); rows ordered (b, t, position). */
 int gtav_attention_temporal(const void* qkv, void* out, int B, int T, int positions, int heads, const float* rot,
                             gtav_stream_t stream);
+/* The last frame of that attention only, against cached context K/V: qkv / out hold the last-frame rows
+ * [B*positions, ...]; kv_cache [B*ctx_frames*positions, 2*heads*64] = (rotated K | V) of window frames
+ * 0..ctx_frames-1, rows ordered (b, t, position); the query sits at window position ctx_frames. */
+int gtav_attention_temporal_last(const void* qkv, void* out, int B, int ctx_frames, int positions, int heads,
+                                 const float* rot, const void* kv_cache, gtav_stream_t stream);
 /* DDIM update of train_dit.py:110-123 over F frames of n elements. */
 int gtav_ddim_update(const float* x, const void* v_bf16, float* out, int F, int n, const float* abar_t,
                      const float* abar_next, const int* final_flag, gtav_stream_t stream);
@@ -130,6 +145,17 @@ int gtav_dit_conditioning(gtav_dit_plan_t p, const int64_t* t, const float* acti
  * out bf16 [B,T,C,H,W]. */
 int gtav_dit_backbone(gtav_dit_plan_t p, const void* x, int x_is_bf16, const int* frame_row, void* out,
                       gtav_stream_t stream);
+/* The backbone split along the frame axis for the sampler's frame cache.  Spatial attention is per frame and
+ * temporal attention is causal over frames (attention.py:62 is_causal=True), so frames 0..T-2 do not depend on
+ * frame T-1:
+ *   gtav_dit_context   runs frames 0..T-2 of every rollout of the window x [B,T,C,H,W] and stores, for every
+ *                      temporal layer, their rotated K and V in the plan's cache (no output; frame_row int32
+ *                      [B*(T-1)] or NULL = identity);
+ *   gtav_dit_last_frame runs frame T-1 only (144*B rows) against that cache; frame_row int32 [B] (NULL =
+ *                      identity); out bf16 [B,C,H,W] = the last frame of what gtav_dit_backbone returns. */
+int gtav_dit_context(gtav_dit_plan_t p, const void* x, int x_is_bf16, const int* frame_row, gtav_stream_t stream);
+int gtav_dit_last_frame(gtav_dit_plan_t p, const void* x, int x_is_bf16, const int* frame_row, void* out,
+                        gtav_stream_t stream);
 /* DiT.forward(x, t, external_cond) = conditioning + backbone with cond_rows == B*T. */
 int gtav_dit_forward(gtav_dit_plan_t p, const void* x, int x_is_bf16, const int64_t* t, const float* actions,
                      void* out, gtav_stream_t stream);
@@ -184,15 +210,21 @@ typedef struct gtav_sampler_s* gtav_sampler_t;
  * table with gtav_dit_conditioning once per generated frame. */
 int gtav_sampler_cond_rows(int B, int T, int steps);
 size_t gtav_sampler_scratch_bytes(int B, int T, int steps);
+enum gtav_sampler_flags {
+    GTAV_SAMPLER_GRAPH = 1,       /* capture the frame's steps into a CUDA graph (stream must not be the legacy default stream) */
+    GTAV_SAMPLER_FRAME_CACHE = 2  /* context pass once per frame + last-frame-only steps (same results, ~4.8x fewer FLOPs) */
+};
 /* x_win: fp32 [B,T,frame_elems] window (caller loads context frames + clamped noise before each frame);
- * v_out: bf16 [B,T,frame_elems]; abar_dev: fp32 alphas_cumprod on device; levels_host: int[steps+1] integer
- * timesteps (linspace(0,999,steps+1) truncated).  This call synchronises `stream` once (copies levels). */
+ * v_out: bf16 [B,T,frame_elems] scratch for the v-prediction; abar_dev: fp32 alphas_cumprod on device;
+ * levels_host: int[steps+1] integer timesteps (linspace(0,999,steps+1) truncated); flags: gtav_sampler_flags.
+ * This call synchronises `stream` once (copies levels). */
 int gtav_sampler_create(gtav_dit_plan_t plan, int B, int T, int steps, int frame_elems, float* x_win, void* v_out,
-                        const float* abar_dev, const int* levels_host, void* scratch, size_t scratch_bytes, int use_graph,
+                        const float* abar_dev, const int* levels_host, void* scratch, size_t scratch_bytes, int flags,
                         gtav_stream_t stream, gtav_sampler_t* out);
 void gtav_sampler_destroy(gtav_sampler_t s);
 /* Runs noise levels steps, steps-1, ..., down to (steps+1-n_steps) on the window (n_steps < 0: all steps+1).
- * With use_graph the step is captured once (stream must not be the legacy default stream) and replayed. */
+ * With GTAV_SAMPLER_GRAPH the first call runs eagerly and captures (synchronising the stream once); later calls
+ * replay one graph per frame (all steps) or per step (partial runs). */
 int gtav_sampler_run_frame(gtav_sampler_t s, int n_steps, gtav_stream_t stream);
 /* x[f*x_stride + i] = clamp(noise[f*n + i], -amax, +amax): the fresh frame of generate.py:201-203. */
 int gtav_noise_clamp(const float* noise, float* x, long x_stride, int F, int n, float amax, gtav_stream_t stream);

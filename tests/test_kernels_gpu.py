@@ -253,3 +253,105 @@ def test_ddim_update_bit_exact(lib):
                                      flag.data_ptr(), N.current_stream()), "ddim")
         ref = ddim_update(x, v.float(), a_t[:, None], a_n[:, None], bool(fin))
         assert torch.equal(out, ref), float((out - ref).abs().max())
+
+
+# ------------------------------------------------------------------------------------------ weight-streaming GEMM
+def run_skinny(lib, A, W, epi, bias=None, res=None, gate=None, frame_row=None, rows_per_frame=144, splits=0, out=None, state=None):
+    N = _N()
+    M, K = A.shape
+    Nn = W.shape[0]
+    if out is None:
+        out = torch.zeros((M, Nn), dtype=torch.bfloat16, device="cuda")
+    if state is None:
+        state = (torch.empty(lib.gtav_gemm_skinny_workspace_bytes(M), dtype=torch.uint8, device="cuda"),
+                 torch.zeros(128, dtype=torch.int32, device="cuda"))
+    ws, counters = state
+    N.check(lib.gtav_gemm_skinny_bf16(A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), out.data_ptr(), out.stride(0), M, Nn, K,
+                                      epi, N.ptr(bias), N.ptr(res), 0 if res is None else res.stride(0), N.ptr(gate),
+                                      0 if gate is None else gate.stride(0), N.ptr(frame_row), rows_per_frame, splits,
+                                      ws.data_ptr(), counters.data_ptr(), N.current_stream()), "gemm_skinny")
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("M,N,K,splits", [
+    (144, 128, 64, 1), (144, 128, 256, 1), (144, 128, 256, 2), (144, 256, 512, 4),       # small: no split, 2- and 4-way split
+    (144, 3072, 1024, 0), (144, 1024, 1024, 0), (144, 4096, 1024, 0), (144, 1024, 4096, 0),   # last-frame shapes at B=1
+    (288, 1024, 1024, 0), (288, 512, 1024, 8), (432, 1024, 1024, 0), (432, 256, 512, 8),       # B = 2, 3 (where the slab fits)
+])
+def test_skinny_gemm_store(lib, M, N, K, splits):
+    g = torch.Generator(device="cuda").manual_seed(M + N * 3 + K * 5)
+    A = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
+    W = (torch.randn((N, K), device="cuda", generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    out = run_skinny(lib, A, W, _N().EPI_STORE, splits=splits)
+    close_bf16(out, A.float() @ W.float().t())
+
+
+def test_skinny_gemm_epilogues_and_reuse(lib):
+    """The fused epilogues, repeated calls on the same workspace/counters (they must reset themselves), in-place residual."""
+    N = _N()
+    M, Nn, K, S = 288, 1024, 1024, 144
+    g = torch.Generator(device="cuda").manual_seed(23)
+    A = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
+    W = (torch.randn((Nn, K), device="cuda", generator=g) / 32).to(torch.bfloat16)
+    bias = (torch.randn((Nn,), device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    res = torch.randn((M, Nn), device="cuda", generator=g).to(torch.bfloat16)
+    gate_tab = torch.randn((5, 3 * Nn), device="cuda", generator=g).to(torch.bfloat16)
+    gate = gate_tab[:, Nn:2 * Nn]
+    frame_row = torch.tensor([3, 1], dtype=torch.int32, device="cuda")
+    state = (torch.empty(lib.gtav_gemm_skinny_workspace_bytes(M), dtype=torch.uint8, device="cuda"),
+             torch.zeros(128, dtype=torch.int32, device="cuda"))
+    y = r16(A.float() @ W.float().t() + bias.float())
+    for _ in range(3):
+        out = run_skinny(lib, A, W, N.EPI_BIAS, bias=bias, state=state)
+        close_bf16(out, y, ulps=3.0, atol=4e-3)
+        out = run_skinny(lib, A, W, N.EPI_BIAS_GELU_TANH, bias=bias, state=state)
+        close_bf16(out, torch.nn.functional.gelu(y, approximate="tanh"), ulps=3.0, atol=4e-3)
+        grow = gate[frame_row.long()].float().repeat_interleave(S, dim=0)
+        ref = res.float() + r16(grow * y)
+        h = res.clone()
+        run_skinny(lib, A, W, N.EPI_BIAS_GATE_RES, bias=bias, res=h, gate=gate, frame_row=frame_row, out=h, state=state)
+        close_bf16(h, ref, ulps=3.0, atol=4e-3, mag=res.float().abs() + (grow * y).abs())
+    assert int(state[1].abs().sum()) == 0                      # rendezvous counters are back to zero
+
+
+def test_skinny_matches_tiled_gemm(lib):
+    """Same inputs through both GEMM kernels: only the fp32 summation order differs."""
+    N = _N()
+    g = torch.Generator(device="cuda").manual_seed(29)
+    A = torch.randn((144, 4096), device="cuda", generator=g).to(torch.bfloat16)
+    W = (torch.randn((1024, 4096), device="cuda", generator=g) / 64).to(torch.bfloat16)
+    a = run_skinny(lib, A, W, N.EPI_STORE)
+    b = run_gemm(lib, A, W, N.EPI_STORE)
+    assert float((a.float() - b.float()).abs().max()) <= 2 ** -7 * float(b.float().abs().max())
+
+
+def test_temporal_attention_last_frame_matches_dense(lib):
+    """attn_temporal_last on cached K/V == the last-frame rows of the dense causal kernel, bit for bit."""
+    N = _N()
+    B, T, P, H = 2, 5, 144, 16
+    D = H * 64
+    g = torch.Generator(device="cuda").manual_seed(31)
+    qkv = torch.randn((B * T * P, 3 * D), device="cuda", generator=g).to(torch.bfloat16)
+    ang = torch.arange(T, device="cuda", dtype=torch.float32)[:, None] * (1.0 / (10000 ** (torch.arange(0, 64, 2, device="cuda").float() / 64)))[None]
+    rot = torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()
+    dense = torch.zeros((B * T * P, D), dtype=torch.bfloat16, device="cuda")
+    N.check(lib.gtav_attention_temporal(qkv.data_ptr(), dense.data_ptr(), B, T, P, H, rot.data_ptr(), N.current_stream()), "dense")
+    # context pass on the first T-1 frames with the cache-writing variant is exercised through the engine
+    # (test_model_gpu.py); here the cache is rebuilt by hand: rotated K (bf16) and V of frames 0..T-2
+    q5 = qkv.view(B, T, P, 3, H, 64)
+    k = q5[:, : T - 1, :, 1].float()
+    kr = torch.empty_like(k)
+    c, s = ang[: T - 1].cos()[None, :, None, None], ang[: T - 1].sin()[None, :, None, None]
+    kr[..., 0::2] = k[..., 0::2] * c - k[..., 1::2] * s
+    kr[..., 1::2] = k[..., 1::2] * c + k[..., 0::2] * s
+    cache = torch.stack([kr.to(torch.bfloat16).reshape(B, T - 1, P, D), q5[:, : T - 1, :, 2].reshape(B, T - 1, P, D)], dim=3).contiguous()
+    last_qkv = q5[:, T - 1].reshape(B * P, 3 * D).contiguous()
+    out = torch.zeros((B * P, D), dtype=torch.bfloat16, device="cuda")
+    import ctypes as C
+    fn = lib.gtav_attention_temporal_last
+    N.check(fn(last_qkv.data_ptr(), out.data_ptr(), B, T - 1, P, H, rot.data_ptr(), cache.data_ptr(), N.current_stream()), "last")
+    torch.cuda.synchronize()
+    ref = dense.view(B, T, P, D)[:, T - 1].reshape(B * P, D)
+    err = float((out.float() - ref.float()).abs().max())
+    assert err <= 2 ** -7 * float(ref.float().abs().max()), err

@@ -78,6 +78,28 @@ def test_dit_forward_bf16_input_and_replan():
         check(v, rp.dit_forward(sd, cfg, x.float(), t, None, rp.BF16), TOL_BF16, f"bf16 input B={B} T={T}")
 
 
+@pytest.mark.parametrize("skinny", ["0", "1"])
+def test_dit_last_frame_split_equals_dense(monkeypatch, skinny):
+    """Context pass + last-frame-only pass (the sampler's frame cache) == the last frame of the dense forward.
+    With the tiled GEMM on both sides (GTAV_SKINNY=0) the two paths run the same arithmetic per row; with the
+    weight-streaming GEMM only the fp32 summation order inside the K splits differs."""
+    from gtav_b200.model.dit import DiT
+    monkeypatch.setenv("GTAV_SKINNY", skinny)
+    sd = make_dit_state(DiTConfig(depth=2), seed=0)
+    model = DiT(depth=2)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    for B, T, seed, actions in ((1, 5, 81, True), (2, 3, 82, False), (1, 2, 83, True), (4, 5, 84, True)):
+        x = seeded_randn((B, T, 16, 18, 32), seed).cuda()
+        t = torch.randint(0, 1000, (B, T), generator=torch.Generator().manual_seed(seed)).cuda()
+        a = w_key_actions(B, T).cuda() if actions else None
+        dense = model(x, t, a)[:, -1:]
+        split = model.forward_last_frame(x, t, a)
+        err = float((dense.float() - split.float()).abs().max())
+        print(f"skinny={skinny} B={B} T={T}: last-frame split vs dense max-abs {err:.5f} equal={torch.equal(dense, split)}")
+        assert err <= (0.0 if skinny == "0" else 2e-2), err
+
+
 def test_dit_rejects_cpu_and_bad_shapes():
     _, model = dit_pair(2)
     with pytest.raises(RuntimeError, match="CUDA"):

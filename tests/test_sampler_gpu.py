@@ -77,7 +77,7 @@ def test_sampler_equals_stepwise_dropin_loop(models):
     acts[1, 3:, 2] = 1.0                                      # actions that change along the rollout
     outs = []
     for use_graph in (True, False):
-        s = Sampler(dit, None, noise_steps=steps, use_graph=use_graph)
+        s = Sampler(dit, None, noise_steps=steps, use_graph=use_graph, frame_cache=False)
         outs.append(s.sample_latents(prompt, acts, total, noise=noise))
         s.close()
     assert torch.equal(outs[0], outs[1])
@@ -92,6 +92,30 @@ def test_sampler_equals_stepwise_dropin_loop(models):
                                  noise_range=noise_range, alphas_cumprod=abar, start_frame=start)
             x[:, -1:] = xp[:, -1:]
     assert torch.equal(outs[0], x), float((outs[0] - x).abs().max())
+
+
+def test_frame_cache_equals_dense_sampling(models):
+    """Context pass + last-frame-only steps reproduce the dense sampler (every step recomputing the whole window):
+    same arithmetic per row, so the latents agree to fp32-summation-order noise of the split-K GEMM."""
+    from gtav_b200.sampler import Sampler
+    dit, _ = models
+    steps, total, n_prompt = 4, 8, 2
+    prompt = torch.randn((2, n_prompt, 16, 18, 32), generator=torch.Generator().manual_seed(15)).cuda()
+    noise = torch.randn((2, total - n_prompt, 16, 18, 32), generator=torch.Generator().manual_seed(16)).cuda()
+    acts = torch.zeros(2, total, 25, device="cuda")
+    acts[:, :, 3] = 1.0
+    acts[1, 4:, 9] = 1.0
+    res = {}
+    for name, kw in (("dense", dict(frame_cache=False)), ("cache", dict(frame_cache=True)),
+                     ("cache_nograph", dict(frame_cache=True, use_graph=False))):
+        s = Sampler(dit, None, noise_steps=steps, **kw)
+        res[name] = s.sample_latents(prompt, acts, total, noise=noise)
+        s.close()
+    assert torch.equal(res["cache"], res["cache_nograph"])
+    err = (res["cache"] - res["dense"]).abs()
+    print(f"frame cache vs dense sampling: max-abs {float(err.max()):.5f} mean-abs {float(err.mean()):.6f} "
+          f"equal={torch.equal(res['cache'], res['dense'])}")
+    assert float(err.max()) < 3e-2 and float(err.mean()) < 2e-3
 
 
 def test_sampler_without_actions_and_growing_window(models):
