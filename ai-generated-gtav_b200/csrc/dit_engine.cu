@@ -366,6 +366,7 @@ int gtav_gemm_skinny_bf16(const void* A, int lda, const void* W, int ldw, void* 
     int rc = skinny_prepare(&op, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), ldw, p, epilogue,
                             static_cast<float*>(workspace), counters, splits);
     if (rc) return rc;
+    if (const char* t = getenv("GTAV_SKINNY_TRACE")) op.trace = reinterpret_cast<long long*>(strtoull(t, nullptr, 0));
     return skinny_run(&op, stream);
 }
 

@@ -35,7 +35,18 @@ struct SkinnyParams {
     int splits, chunks, tiles;
     float* ws;
     int* counters;
+    long long* trace;      // optional [gridDim.x][8] globaltimer stamps (ns) of the phase boundaries; null in production
 };
+
+__device__ __forceinline__ long long globaltimer_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define SK_STAMP(slot)                                                                     \
+    do {                                                                                   \
+        if (p.trace != nullptr) p.trace[static_cast<size_t>(blockIdx.x) * 8 + (slot)] = globaltimer_ns(); \
+    } while (0)
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     int v;
@@ -62,6 +73,57 @@ __device__ __forceinline__ void skinny_store(const GemmParams& g, int tok, int n
     g.out[static_cast<size_t>(tok) * g.ldo + n] = __float2bfloat16_rn(y);
 }
 
+// Four consecutive output columns n..n+3 of token `tok` (split-K reduce path: 8-byte vector accesses).
+template <int EPI>
+__device__ __forceinline__ void skinny_store4(const GemmParams& g, int tok, int n, float4 acc) {
+    float y[4] = {acc.x, acc.y, acc.z, acc.w};
+    if (EPI != EPI_STORE) {
+        const uint2 bv = *reinterpret_cast<const uint2*>(g.bias + n);
+        const float2 b0 = unpack_bf16x2(bv.x), b1 = unpack_bf16x2(bv.y);
+        y[0] += b0.x; y[1] += b0.y; y[2] += b1.x; y[3] += b1.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = bf16_round(y[j]);
+    if (EPI == EPI_BIAS_GELU_TANH) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = gelu_tanh_f(y[j]);
+    } else if (EPI == EPI_BIAS_GATE_RES) {
+        int f = tok / g.rows_per_frame;
+        if (g.frame_row != nullptr) f = g.frame_row[f];
+        const uint2 gv = *reinterpret_cast<const uint2*>(g.gate + static_cast<size_t>(f) * g.gate_ld + n);
+        const uint2 rv = *reinterpret_cast<const uint2*>(g.res + static_cast<size_t>(tok) * g.ldr + n);
+        const float2 g0 = unpack_bf16x2(gv.x), g1 = unpack_bf16x2(gv.y), r0 = unpack_bf16x2(rv.x), r1 = unpack_bf16x2(rv.y);
+        y[0] = r0.x + bf16_round(g0.x * y[0]);
+        y[1] = r0.y + bf16_round(g0.y * y[1]);
+        y[2] = r1.x + bf16_round(g1.x * y[2]);
+        y[3] = r1.y + bf16_round(g1.y * y[3]);
+    }
+    uint2 o;
+    o.x = pack_bf16x2(y[0], y[1]);
+    o.y = pack_bf16x2(y[2], y[3]);
+    *reinterpret_cast<uint2*>(g.out + static_cast<size_t>(tok) * g.ldo + n) = o;
+}
+
+// Sum the S partial tiles of this row block for tokens lo + wid, lo + wid + 8, ... (one warp per token, lane = 4
+// consecutive weight rows) in split order and run the epilogue.  S is a template parameter so that all S loads of a
+// token are in flight together: the loop is otherwise a chain of exposed L2 latencies.
+template <int EPI, int S>
+__device__ __forceinline__ void skinny_reduce(const GemmParams& g, const float* part, int total, int lo, int hi, int wid, int lane,
+                                              int n0) {
+    const float* base = part + 4 * lane;
+#pragma unroll 1
+    for (int tok = lo + wid; tok < hi; tok += 8) {
+        float4 v[S];
+#pragma unroll
+        for (int s2 = 0; s2 < S; ++s2)
+            v[s2] = __ldcg(reinterpret_cast<const float4*>(base + (static_cast<size_t>(s2) * total + tok) * 128));
+        float4 acc = v[0];
+#pragma unroll
+        for (int s2 = 1; s2 < S; ++s2) { acc.x += v[s2].x; acc.y += v[s2].y; acc.z += v[s2].z; acc.w += v[s2].w; }
+        skinny_store4<EPI>(g, tok, n0 + 4 * lane, acc);
+    }
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const SkinnyParams p) {
@@ -76,6 +138,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 128) SK_STAMP(0);                                       // kernel entry
     const int rb = blockIdx.x / S, split = blockIdx.x - rb * S;
     const int kc0 = split * chunks;
     const uint32_t tmem_cols = tiles * SK_NT <= 256 ? 256u : 512u;
@@ -97,6 +160,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_trigger();
+    if (threadIdx.x == 128) SK_STAMP(1);                                       // set-up done
 
     if (warp == 0) {
         if (lane == 0) {
@@ -116,8 +180,10 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(128, SK_NT);
             mbar_wait(bar_w, 0);
+            SK_STAMP(2);                                                       // W slab landed
             for (int t = 0; t < tiles; ++t) {
                 mbar_wait(&bar_a[t], 0);
+                if (t == 0) SK_STAMP(3);                                       // first A tile landed
                 tcgen05_fence_after();
                 for (int ch = 0; ch < chunks; ++ch) {
                     const uint64_t dw = umma_desc_sw128(smem_u32(sW + ch * SK_W_CHUNK));
@@ -141,6 +207,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         if (EPI != EPI_STORE) bias_n = __bfloat162float(g.bias[n]);
         mbar_wait(bar_acc, 0);
         tcgen05_fence_after();
+        if (threadIdx.x == 128) SK_STAMP(4);                                   // accumulator complete
         const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         if (S == 1) {
 #pragma unroll 1
@@ -165,6 +232,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             epi_bar_sync();
             int* arrive = p.counters + 2 * rb;
             if (threadIdx.x == 128) {
+                SK_STAMP(5);                                                   // partials written + fenced
                 atomicAdd(arrive, 1);
                 uint32_t spins = 0;
                 while (ld_acquire_gpu(arrive) < S) {
@@ -175,23 +243,33 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
                     }
                 }
             }
-            epi_bar_sync();
-            const int lo = split * total / S, hi = (split + 1) * total / S;
-            const float* part = p.ws + static_cast<size_t>(rb) * S * total * 128 + row;
-#pragma unroll 1
-            for (int tok = lo; tok < hi; ++tok) {
-                float acc = 0.f;
-                for (int s2 = 0; s2 < S; ++s2) acc += __ldcg(part + (static_cast<size_t>(s2) * total + tok) * 128);
-                skinny_store<EPI>(g, tok, n, acc, bias_n);
-            }
-            epi_bar_sync();
-            if (threadIdx.x == 128) {
-                const int old = atomicAdd(arrive + 1, 1);
-                if (old == S - 1) {                       // everyone of this row block is past the rendezvous
-                    arrive[1] = 0;
-                    __threadfence();
-                    atomicExch(arrive, 0);
-                }
+        }
+    }
+    if (S > 1) {
+        // all 8 warps reduce: warps 0-3 get here as soon as their producer / MMA roles are done and wait for the
+        // epilogue warps, which arrive once the rendezvous of the row block has completed
+        __syncthreads();
+        if (threadIdx.x == 128) SK_STAMP(6);                                   // rendezvous passed
+        const GemmParams& g = p.g;
+        const int total = tiles * SK_NT;
+        const int lo = split * total / S, hi = (split + 1) * total / S;
+        const float* part = p.ws + static_cast<size_t>(rb) * S * total * 128;
+        switch (S) {
+            case 2: skinny_reduce<EPI, 2>(g, part, total, lo, hi, warp, lane, rb * 128); break;
+            case 4: skinny_reduce<EPI, 4>(g, part, total, lo, hi, warp, lane, rb * 128); break;
+            case 8: skinny_reduce<EPI, 8>(g, part, total, lo, hi, warp, lane, rb * 128); break;
+            case 16: skinny_reduce<EPI, 16>(g, part, total, lo, hi, warp, lane, rb * 128); break;
+            default: __trap();
+        }
+        __syncthreads();
+        if (threadIdx.x == 128) {
+            SK_STAMP(7);                                                       // reduced + stored
+            int* arrive = p.counters + 2 * rb;
+            const int old = atomicAdd(arrive + 1, 1);
+            if (old == S - 1) {                           // everyone of this row block is past the rendezvous
+                arrive[1] = 0;
+                __threadfence();
+                atomicExch(arrive, 0);
             }
         }
     }
@@ -221,7 +299,7 @@ int skinny_pick_splits(int M, int N, int K) {
     const int tiles = M / SK_NT, rbs = N / 128, kchunks = K / 64;
     const int per_chunk = SK_W_CHUNK + tiles * SK_A_CHUNK;
     int best = 0;
-    for (int s = 1; s <= kchunks; ++s) {
+    for (int s = 1; s <= 16; s *= 2) {                 // the reduction is instantiated for S = 1, 2, 4, 8, 16
         if (kchunks % s) continue;
         if ((kchunks / s) * per_chunk > SK_SMEM_BUDGET) continue;
         if (rbs * s > sms) break;
@@ -245,7 +323,7 @@ int skinny_prepare(SkinnyOp* op, const bf16* A, int lda, const bf16* W, int ldw,
     const int tiles = p.M / SK_NT, rbs = p.N / 128, kchunks = p.K / 64;
     const int per_chunk = SK_W_CHUNK + tiles * SK_A_CHUNK;
     int S = splits_override > 0 ? splits_override : skinny_pick_splits(p.M, p.N, p.K);
-    if (S <= 0 || kchunks % S || (kchunks / S) * per_chunk > SK_SMEM_BUDGET || rbs * S > 160 || rbs > 64) {
+    if (S <= 0 || S > 16 || (S & (S - 1)) || kchunks % S || (kchunks / S) * per_chunk > SK_SMEM_BUDGET || rbs * S > 160 || rbs > 64) {
         set_error("skinny gemm: no valid K split for M=%d N=%d K=%d (S=%d)", p.M, p.N, p.K, S);
         return -1;
     }
@@ -256,6 +334,7 @@ int skinny_prepare(SkinnyOp* op, const bf16* A, int lda, const bf16* W, int ldw,
     op->tiles = tiles;
     op->ws = ws;
     op->counters = counters;
+    op->trace = nullptr;
     int rc = make_tmap_3d(&op->tmW, W, p.N, p.K, ldw, 128, op->chunks);
     if (rc) return rc;
     return make_tmap_3d(&op->tmA, A, p.M, p.K, lda, SK_NT, op->chunks);
@@ -271,6 +350,7 @@ static int skinny_launch(const SkinnyOp* op, cudaStream_t stream) {
     }
     SkinnyParams sp;
     sp.g = op->p; sp.splits = op->splits; sp.chunks = op->chunks; sp.tiles = op->tiles; sp.ws = op->ws; sp.counters = op->counters;
+    sp.trace = op->trace;
     // At least half of the SM's shared memory, so that exactly one CTA of this kernel fits on an SM: the CTAs of a
     // row block wait for each other, and a second CTA on the same SM could block in tcgen05.alloc behind a waiting one.
     size_t smem = static_cast<size_t>(op->chunks) * (SK_W_CHUNK + op->tiles * SK_A_CHUNK) + 64 + 1024;

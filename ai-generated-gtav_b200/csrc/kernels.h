@@ -91,6 +91,7 @@ struct SkinnyOp {
     int epi, splits, chunks, tiles;
     float* ws;        // fp32 partial-sum workspace, skinny_workspace_bytes(M)
     int* counters;    // 128 zero-initialised ints (rendezvous counters, self-resetting)
+    long long* trace; // optional phase time stamps [CTAs][8] (profiling aid), normally null
 };
 bool skinny_supported(int M, int N, int K, int epi);
 int skinny_pick_splits(int M, int N, int K);
