@@ -52,7 +52,8 @@ attn_seq_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads,
     const bf16* kbase = qbase + heads * HD;
     const bf16* vbase = kbase + heads * HD;
 
-    // ---- Q fragments (16 rows x 64 dims per warp), rotary applied in registers -----------------
+    // ---- Q fragments (16 rows x 64 dims per warp): raw loads first, rotary applied once the K/V loads of the
+    // first key block are in flight too (one global round trip for everything the block needs) ------------------
     const int q0 = (blockIdx.x * WARPS + warp) * 16;        // first query row of this warp (within the group)
     uint32_t qf[4][4];
 #pragma unroll
@@ -61,10 +62,7 @@ attn_seq_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads,
         for (int h = 0; h < 4; ++h) {
             const int r = q0 + g + (h & 1) * 8;
             const int c = ks * 16 + 2 * tig + (h >> 1) * 8;
-            uint32_t u = *reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(r) * ld + c);
-            const int pr = c >> 1;
-            if (pr < ROT_PAIRS) u = rotate_pair(u, rot[r * ROT_PAIRS + pr]);
-            qf[ks][h] = u;
+            qf[ks][h] = *reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(r) * ld + c);
         }
     }
 
@@ -76,25 +74,44 @@ attn_seq_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads,
     float m_run[2] = {-INFINITY, -INFINITY};
     float l_run[2] = {0.f, 0.f};
     const float sl2 = 0.125f * 1.4426950408889634f;          // 1/sqrt(64) * log2(e)
+    constexpr int STAGE_ITERS = (KB * 8) / (WARPS * 32);
+    static_assert((KB * 8) % (WARPS * 32) == 0, "staging loop must divide evenly");
 
     for (int kb0 = 0; kb0 < SEQ; kb0 += KB) {
         if (kb0 > 0) __syncthreads();                        // previous block fully consumed
-        // ---- stage K (rotated) and V for keys [kb0, kb0+KB) ---------------------------------
-#pragma unroll 4
-        for (int i = threadIdx.x; i < KB * 8; i += WARPS * 32) {
+        // ---- stage K (rotated) and V for keys [kb0, kb0+KB): all loads issued before any is consumed ----------
+        uint4 kraw[STAGE_ITERS], vraw[STAGE_ITERS];
+#pragma unroll
+        for (int it = 0; it < STAGE_ITERS; ++it) {
+            const int i = threadIdx.x + it * WARPS * 32;
             const int r = i >> 3, c8 = (i & 7) * 8;
             const size_t goff = static_cast<size_t>(kb0 + r) * ld + c8;
-            uint4 kv = *reinterpret_cast<const uint4*>(kbase + goff);
-            const uint4 vv = *reinterpret_cast<const uint4*>(vbase + goff);
-            uint32_t kw[4] = {kv.x, kv.y, kv.z, kv.w};
+            kraw[it] = *reinterpret_cast<const uint4*>(kbase + goff);
+            vraw[it] = *reinterpret_cast<const uint4*>(vbase + goff);
+        }
+        if (kb0 == 0) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const int r = q0 + g + (h & 1) * 8;
+                    const int pr = (ks * 16 + 2 * tig + (h >> 1) * 8) >> 1;
+                    if (pr < ROT_PAIRS) qf[ks][h] = rotate_pair(qf[ks][h], rot[r * ROT_PAIRS + pr]);
+                }
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < STAGE_ITERS; ++it) {
+            const int i = threadIdx.x + it * WARPS * 32;
+            const int r = i >> 3, c8 = (i & 7) * 8;
+            uint32_t kw[4] = {kraw[it].x, kraw[it].y, kraw[it].z, kraw[it].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int pr = (c8 >> 1) + j;
                 if (pr < ROT_PAIRS) kw[j] = rotate_pair(kw[j], rot[(kb0 + r) * ROT_PAIRS + pr]);
             }
-            kv = make_uint4(kw[0], kw[1], kw[2], kw[3]);
-            *reinterpret_cast<uint4*>(&sK[r * SROW + c8]) = kv;
-            *reinterpret_cast<uint4*>(&sV[r * SROW + c8]) = vv;
+            *reinterpret_cast<uint4*>(&sK[r * SROW + c8]) = make_uint4(kw[0], kw[1], kw[2], kw[3]);
+            *reinterpret_cast<uint4*>(&sV[r * SROW + c8]) = vraw[it];
         }
         __syncthreads();
 
@@ -185,7 +202,8 @@ int launch_attention_seq(const bf16* qkv, bf16* out, int groups, int seq, int he
                          cudaStream_t s) {
     if (groups <= 0) return 0;
     if (seq == 144 && rot_pairs == 32) {
-        // all 144 keys of a head staged in one pass (one global round trip), queries split over 3 CTAs
+        // all 144 keys of a head staged in one pass (every global load of the block in flight at once); the queries
+        // are split over 3 CTAs of 3 warps so that 48 SMs share the loads at B = 1
         GTAV_CUDA_OK(launch_k(attn_seq_kernel<144, 144, 3, 32>, dim3(3, heads, groups), dim3(3 * 32), 0, s, qkv, out, heads, rot));
     } else if (seq == 576 && rot_pairs == 16) {
         GTAV_CUDA_OK(launch_k(attn_seq_kernel<576, 64, 4, 16>, dim3(9, heads, groups), dim3(4 * 32), 0, s, qkv, out, heads, rot));

@@ -143,6 +143,14 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorM
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
         : "memory");
 }
+// Pull this thread's share of [ptr, ptr + total) into L2 with per-line prefetch instructions (LSU path: the TMA
+// unit stays free for the operand loads).  `part` of `parts` participating threads, 128-byte lines.
+__device__ __forceinline__ void l2_prefetch_share(const void* ptr, size_t total, int part, int parts) {
+    if (ptr == nullptr || total == 0) return;
+    const char* base = static_cast<const char*>(ptr);
+    const size_t lines = (total + 127) >> 7;
+    for (size_t l = part; l < lines; l += parts) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (l << 7)));
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)

@@ -108,10 +108,15 @@ int build_shape(gtav_dit_plan_s* p, Shape* sh, int frames, bool allow_skinny) {
     rc |= gemm_prepare(&sh->g_patch, p->xa, 64, static_cast<const bf16*>(w.patch_w), 64, gp(p->h, D, w.patch_b, M, D, 64), EPI_BIAS);
     const int nh = 2 * h->cfg.depth;
     sh->g_qkv.resize(nh); sh->g_out.resize(nh); sh->g_fc1.resize(nh); sh->g_fc2.resize(nh);
+    // The split-K weight-streaming kernel wins where K is long and N short (fc2: 8.6 vs 17.7 us at M = 144, in-graph,
+    // B200); for the K = 1024 GEMMs the tiled kernel's direct epilogue beats the partial-sum exchange (6-8 vs 8-10 us).
+    // GTAV_SKINNY=all forces it everywhere it fits, GTAV_SKINNY=0 nowhere.
     const bool sk_ok = allow_skinny && skinny_enabled() && p->sk_ws != nullptr;
-    sh->sk[0] = sk_ok && skinny_pick_splits(M, 3 * D, D) > 0;
-    sh->sk[1] = sk_ok && skinny_pick_splits(M, D, D) > 0;
-    sh->sk[2] = sk_ok && skinny_pick_splits(M, 4 * D, D) > 0;
+    const char* skenv = getenv("GTAV_SKINNY");
+    const bool sk_all = skenv != nullptr && skenv[0] == 'a';
+    sh->sk[0] = sk_ok && sk_all && skinny_pick_splits(M, 3 * D, D) > 0;
+    sh->sk[1] = sk_ok && sk_all && skinny_pick_splits(M, D, D) > 0;
+    sh->sk[2] = sk_ok && sk_all && skinny_pick_splits(M, 4 * D, D) > 0;
     sh->sk[3] = sk_ok && skinny_pick_splits(M, D, 4 * D) > 0;
     if (sh->sk[0]) sh->s_qkv.resize(nh);
     if (sh->sk[1]) sh->s_out.resize(nh);
@@ -120,12 +125,21 @@ int build_shape(gtav_dit_plan_s* p, Shape* sh, int frames, bool allow_skinny) {
     for (int i = 0; i < nh && rc == 0; ++i) {
         const gtav_dit_half& hw = h->halves[i];
         const bf16* modl = p->mod + static_cast<size_t>(i) * 6 * D;
-        const GemmParams pq = gp(p->qkv, 3 * D, nullptr, M, 3 * D, D);
+        GemmParams pq = gp(p->qkv, 3 * D, nullptr, M, 3 * D, D);
         GemmParams po = gp(p->h, D, hw.out_b, M, D, D);
         po.res = p->h; po.ldr = D; po.gate = modl + 2 * D; po.gate_ld = W; po.rows_per_frame = S;
-        const GemmParams p1 = gp(p->mlp, 4 * D, hw.fc1_b, M, 4 * D, D);
+        GemmParams p1 = gp(p->mlp, 4 * D, hw.fc1_b, M, 4 * D, D);
         GemmParams p2 = gp(p->h, D, hw.fc2_b, M, D, 4 * D);
         p2.res = p->h; p2.ldr = D; p2.gate = modl + 5 * D; p2.gate_ld = W; p2.rows_per_frame = S;
+        // each GEMM pulls the next one's weights into L2 while it runs (weights: 2 bytes per element)
+        const size_t DD = static_cast<size_t>(D) * D * 2;
+        const char* pfenv = getenv("GTAV_PREFETCH");
+        if (!(pfenv != nullptr && pfenv[0] == '0')) {
+            pq.prefetch = hw.out_w; pq.prefetch_bytes = DD;
+            po.prefetch = hw.fc1_w; po.prefetch_bytes = 4 * DD;
+            p1.prefetch = hw.fc2_w; p1.prefetch_bytes = 4 * DD;
+            if (i + 1 < nh) { p2.prefetch = h->halves[i + 1].qkv_w; p2.prefetch_bytes = 3 * DD; }
+        }
         if (sh->sk[0]) rc |= skinny_prepare(&sh->s_qkv[i], p->hn, D, static_cast<const bf16*>(hw.qkv_w), D, pq, EPI_STORE, p->sk_ws, p->sk_counters);
         else rc |= gemm_prepare(&sh->g_qkv[i], p->hn, D, static_cast<const bf16*>(hw.qkv_w), D, pq, EPI_STORE);
         if (sh->sk[1]) rc |= skinny_prepare(&sh->s_out[i], p->att, D, static_cast<const bf16*>(hw.out_w), D, po, EPI_BIAS_GATE_RES, p->sk_ws, p->sk_counters);

@@ -197,6 +197,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         }
         pdl_wait();
     } else if (warp >= 4) {
+        // idle until the accumulator is ready: pull the NEXT GEMM's weights into L2 meanwhile
+        l2_prefetch_share(p.g.prefetch, p.g.prefetch_bytes, (blockIdx.x * 4 + (warp - 4)) * 32 + lane, gridDim.x * 128);
         pdl_wait();
         const GemmParams& g = p.g;
         const int q = warp & 3;

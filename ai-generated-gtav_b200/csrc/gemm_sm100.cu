@@ -5,12 +5,18 @@
 // with the surrounding elementwise ops (bias, GELU/SiLU, adaLN gate, residual) fused as epilogues that
 // round to bf16 exactly where the reference's autocast graph does.
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
-//   warp 0   : TMA producer  - cp.async.bulk.tensor 2-D tiles of A (128x64) and W (BNx64), 128B swizzle
+// Structure (one 128 x BN output tile per CTA, 224 threads):
+//   warp 0   : TMA producer of A - one cp.async.bulk.tensor per stage: KC consecutive 64-wide K chunks of 128 rows
+//   warp 6   : TMA producer of W - the same for BN weight rows; runs ahead of the previous kernel (PDL): weights
+//              do not depend on it
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1)
 //   warps 2-5: epilogue      - tcgen05.ld 32x32b from their TMEM lane quadrant, fused math, 16-byte stores
-// smem full/empty mbarrier ring between producer and issuer; tcgen05.commit frees slots and signals
+// smem full/empty mbarrier ring between the producers and the issuer; tcgen05.commit frees slots and signals
 // the epilogue.  Out-of-range rows / columns / K are zero-filled by TMA and masked in the epilogue.
+// Why two producers and multi-chunk boxes: measured on B200 (scripts/probe_tma*.cu, profiles/r01), one warp gets a
+// bulk-tensor copy accepted only every ~0.4 us whatever its size and an SM runs two at a time, so a stage made of
+// two 16 KB boxes issued by one thread caps a CTA at ~45 GB/s (5x short of what a 128x128 tile needs); two warps
+// issuing 32 KB boxes (KC = 2, via a [64 | rows | K/64] 3-D view) reach ~160 GB/s per SM.
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -21,13 +27,15 @@
 namespace gtav {
 
 static constexpr int BM = 128;
-static constexpr int BK = 64;
-static constexpr int GEMM_THREADS = 192;
+static constexpr int BK = 64;                 // one 128-byte-swizzled chunk
+static constexpr int GEMM_THREADS = 224;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int KC>
 struct GemmSmem {
-    static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int A_CHUNK = BM * BK * 2;
+    static constexpr int B_CHUNK = BN * BK * 2;
+    static constexpr int A_BYTES = KC * A_CHUNK;           // per stage
+    static constexpr int B_BYTES = KC * B_CHUNK;
     static constexpr int BAR_OFF = STAGES * (A_BYTES + B_BYTES);
     static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;   // +1024: manual alignment slack
 };
@@ -110,10 +118,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
     }
 }
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int KC, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-    using L = GemmSmem<BN, STAGES>;
+    using L = GemmSmem<BN, STAGES, KC>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
@@ -127,16 +135,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int lane = threadIdx.x & 31;
     const int n_blk = blockIdx.x;
     const int m_blk = blockIdx.y;
-    const int num_kb = (p.K + BK - 1) / BK;
+    const int num_ks = (p.K + KC * BK - 1) / (KC * BK);      // pipeline stages along K (KC chunks each)
 
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
-    }
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tmA);
+    if (warp == 6 && lane == 0) tma_prefetch_desc(&tmB);
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < STAGES; ++s) {
-                mbar_init(&full_bar[s], 1);
+                mbar_init(&full_bar[s], 2);           // one arrive.expect_tx per producer
                 mbar_init(&empty_bar[s], 1);
             }
             mbar_init(accum_bar, 1);
@@ -153,40 +159,44 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     pdl_trigger();                                // the next kernel may start its own set-up now
 
     if (warp == 0) {
+        pdl_wait();                               // A is the previous kernel's output
         if (lane == 0) {
-            // W tiles are weights (never written by the kernel before us): start streaming them before
-            // waiting for the previous kernel, so HBM latency overlaps its tail.  A waits.
-            const int pre = num_kb < STAGES ? num_kb : STAGES;
-            for (int kb = 0; kb < pre; ++kb) {
-                mbar_arrive_expect_tx(&full_bar[kb], L::A_BYTES + L::B_BYTES);
-                tma_load_2d(sB + kb * L::B_BYTES, &tmB, &full_bar[kb], kb * BK, n_blk * BN);
+            for (int ks = 0; ks < num_ks; ++ks) {
+                const int s = ks % STAGES;
+                mbar_wait(&empty_bar[s], ((ks / STAGES) & 1) ^ 1);
+                mbar_arrive_expect_tx(&full_bar[s], L::A_BYTES);
+                if (KC == 1) tma_load_2d(sA + s * L::A_BYTES, &tmA, &full_bar[s], ks * BK, m_blk * BM);
+                else tma_load_3d(sA + s * L::A_BYTES, &tmA, &full_bar[s], 0, m_blk * BM, ks * KC);
             }
-            pdl_wait();
-            for (int kb = 0; kb < pre; ++kb) tma_load_2d(sA + kb * L::A_BYTES, &tmA, &full_bar[kb], kb * BK, m_blk * BM);
-            for (int kb = pre; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_arrive_expect_tx(&full_bar[s], L::A_BYTES + L::B_BYTES);
-                tma_load_2d(sA + s * L::A_BYTES, &tmA, &full_bar[s], kb * BK, m_blk * BM);
-                tma_load_2d(sB + s * L::B_BYTES, &tmB, &full_bar[s], kb * BK, n_blk * BN);
+        }
+    } else if (warp == 6) {
+        if (lane == 0) {
+            // weights are never written by the kernel before us: stream them without waiting for it
+            for (int ks = 0; ks < num_ks; ++ks) {
+                const int s = ks % STAGES;
+                mbar_wait(&empty_bar[s], ((ks / STAGES) & 1) ^ 1);
+                mbar_arrive_expect_tx(&full_bar[s], L::B_BYTES);
+                if (KC == 1) tma_load_2d(sB + s * L::B_BYTES, &tmB, &full_bar[s], ks * BK, n_blk * BN);
+                else tma_load_3d(sB + s * L::B_BYTES, &tmB, &full_bar[s], 0, n_blk * BN, ks * KC);
             }
         }
         pdl_wait();
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+            for (int ks = 0; ks < num_ks; ++ks) {
+                const int s = ks % STAGES;
+                mbar_wait(&full_bar[s], (ks / STAGES) & 1);
                 tcgen05_fence_after();
-                const uint64_t da = umma_desc_sw128(smem_u32(sA + s * L::A_BYTES));
-                const uint64_t db = umma_desc_sw128(smem_u32(sB + s * L::B_BYTES));
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    // +32 bytes (16 bf16) along K inside the 128-byte swizzle row: +2 in 16-byte units
-                    umma_bf16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                for (int c = 0; c < KC; ++c) {
+                    const uint64_t da = umma_desc_sw128(smem_u32(sA + s * L::A_BYTES + c * L::A_CHUNK));
+                    const uint64_t db = umma_desc_sw128(smem_u32(sB + s * L::B_BYTES + c * L::B_CHUNK));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // +32 bytes (16 bf16) along K inside the 128-byte swizzle row: +2 in 16-byte units
+                        umma_bf16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (ks | c | k) != 0 ? 1u : 0u);
+                    }
                 }
                 umma_commit(&empty_bar[s]);       // slot reusable once these MMAs have read it
             }
@@ -194,6 +204,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         pdl_wait();
     } else {
+        // idle until the accumulator is ready: pull the NEXT GEMM's weights into L2 meanwhile
+        l2_prefetch_share(p.prefetch, p.prefetch_bytes, ((blockIdx.y * gridDim.x + blockIdx.x) * 4 + (warp - 2)) * 32 + lane,
+                          gridDim.x * gridDim.y * 128);
         pdl_wait();                               // bias / gate / residual may come from the previous kernel
         const int q = warp & 3;                   // TMEM lane quadrant this warp may read
         const int row = m_blk * BM + q * 32 + lane;
@@ -340,16 +353,23 @@ int gemm_prepare(GemmOp* op, const bf16* A, int lda, const bf16* W, int ldw, con
     op->p = p;
     op->bn = bn;
     op->epi = epi;
-    int rc = make_tmap(&op->tmA, A, p.M, p.K, lda, BM);
+    // two 64-wide K chunks per TMA instruction whenever K allows the [64 | rows | K/64] view
+    op->kc = (p.K % BK == 0 && p.K >= 2 * BK) ? 2 : 1;
+    if (op->kc == 1) {
+        int rc = make_tmap(&op->tmA, A, p.M, p.K, lda, BM);
+        if (rc) return rc;
+        return make_tmap(&op->tmB, W, p.N, p.K, ldw, bn);
+    }
+    int rc = make_tmap_3d(&op->tmA, A, p.M, p.K, lda, BM, op->kc);
     if (rc) return rc;
-    return make_tmap(&op->tmB, W, p.N, p.K, ldw, bn);
+    return make_tmap_3d(&op->tmB, W, p.N, p.K, ldw, bn, op->kc);
 }
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int KC, int EPI>
 static int launch_one(const GemmOp* op, cudaStream_t stream) {
-    using L = GemmSmem<BN, STAGES>;
+    using L = GemmSmem<BN, STAGES, KC>;
     static bool configured = false;
-    auto kern = gemm_bf16_kernel<BN, STAGES, EPI>;
+    auto kern = gemm_bf16_kernel<BN, STAGES, KC, EPI>;
     if (!configured) {
         GTAV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         configured = true;
@@ -361,10 +381,17 @@ static int launch_one(const GemmOp* op, cudaStream_t stream) {
 
 template <int EPI>
 static int launch_epi(const GemmOp* op, cudaStream_t stream) {
+    if (op->kc == 2) {
+        switch (op->bn) {
+            case 64: return launch_one<64, 4, 2, EPI>(op, stream);       // 4 x 48 KB
+            case 128: return launch_one<128, 3, 2, EPI>(op, stream);     // 3 x 64 KB
+            default: return launch_one<256, 2, 2, EPI>(op, stream);      // 2 x 96 KB
+        }
+    }
     switch (op->bn) {
-        case 64: return launch_one<64, 4, EPI>(op, stream);
-        case 128: return launch_one<128, 3, EPI>(op, stream);
-        default: return launch_one<256, 4, EPI>(op, stream);
+        case 64: return launch_one<64, 4, 1, EPI>(op, stream);
+        case 128: return launch_one<128, 3, 1, EPI>(op, stream);
+        default: return launch_one<256, 4, 1, EPI>(op, stream);
     }
 }
 

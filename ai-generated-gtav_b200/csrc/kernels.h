@@ -61,12 +61,17 @@ struct GemmParams {
     const int* frame_row;               // null => identity
     int rows_per_frame;
     int M, N, K;
+    // Weights of the NEXT GEMM in the stream (or null): every CTA asks the TMA unit to pull its share into L2 at
+    // kernel start, so the next kernel's first loads are L2 hits instead of ~2 us HBM round trips.
+    const void* prefetch;
+    size_t prefetch_bytes;
 };
 
 struct GemmOp {
     CUtensorMap tmA, tmB;
     GemmParams p;
     int bn;      // tile width chosen at prepare time (64 / 128 / 256)
+    int kc;      // 64-wide K chunks per TMA instruction / pipeline stage (1: 2-D maps, any K; 2: 3-D maps, K % 64 == 0)
     int epi;
 };
 

@@ -24,12 +24,26 @@ ln_rows_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int M, const 
     const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
     if (row >= M) return;
     const bf16* xr = x + static_cast<size_t>(row) * D;
+    // issue every global load of the row up front (x, and the shift / scale vectors whose address hangs off
+    // frame_row): the kernel is a chain of memory round trips otherwise
+    uint4 xu[CHUNKS], shu[CHUNKS], scu[CHUNKS];
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) xu[c] = *reinterpret_cast<const uint4*>(xr + c * 256 + lane * 8);
+    if (!AFFINE) {
+        int f = row / rows_per_frame;
+        if (frame_row != nullptr) f = frame_row[f];
+        const bf16* mrow = mod + static_cast<size_t>(f) * mod_ld;
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+            shu[c] = *reinterpret_cast<const uint4*>(mrow + shift_off + c * 256 + lane * 8);
+            scu[c] = *reinterpret_cast<const uint4*>(mrow + scale_off + c * 256 + lane * 8);
+        }
+    }
     float v[CHUNKS][8];
     float sum = 0.f;
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
-        uint4 u = *reinterpret_cast<const uint4*>(xr + c * 256 + lane * 8);
-        const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+        const uint32_t uw[4] = {xu[c].x, xu[c].y, xu[c].z, xu[c].w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float2 f = unpack_bf16x2(uw[j]);
@@ -49,12 +63,6 @@ ln_rows_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int M, const 
         }
     const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + 1e-6f);
 
-    const bf16* mrow = nullptr;
-    if (!AFFINE) {
-        int f = row / rows_per_frame;
-        if (frame_row != nullptr) f = frame_row[f];
-        mrow = mod + static_cast<size_t>(f) * mod_ld;
-    }
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
         const int col = c * 256 + lane * 8;
@@ -67,8 +75,7 @@ ln_rows_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int M, const 
 #pragma unroll
             for (int j = 0; j < 8; ++j) y[j] = (v[c][j] - mean) * rstd * ww[j] + bb[j];
         } else {
-            const uint4 sh = *reinterpret_cast<const uint4*>(mrow + shift_off + col);
-            const uint4 sc = *reinterpret_cast<const uint4*>(mrow + scale_off + col);
+            const uint4 sh = shu[c], sc = scu[c];
             const uint32_t shw[4] = {sh.x, sh.y, sh.z, sh.w}, scw[4] = {sc.x, sc.y, sc.z, sc.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {

@@ -25,6 +25,7 @@ NW = 32
 def graph_time(calls, reps=5):
     """calls: list of zero-arg launchers, captured in order into one graph.  Returns us per launch."""
     s = torch.cuda.Stream()
+    torch.cuda.synchronize()                     # a plan's workspace must not be used from two streams at once
     with torch.cuda.stream(s):
         for c in calls[: min(len(calls), 8)]:
             c()                                  # first-use configuration outside capture
@@ -112,7 +113,56 @@ def report(name, us, **kw):
     print(json.dumps(dict(kernel=name, us_per_launch=round(us, 2), **kw)), flush=True)
 
 
+def engine_steps():
+    """The real last-frame step (gtav_dit_last_frame of a 16-block DiT, B=1, T=5) replayed from a graph, under the
+    engine's environment switches."""
+    import ctypes as C
+    from gtav_b200.model.dit import DiT_models
+    torch.manual_seed(0)
+    x = torch.randn((1, 5, 16, 18, 32), device=dev)
+    t = torch.tensor([[15, 15, 15, 15, 500]], device=dev)
+    rows = torch.arange(5, dtype=torch.int32, device=dev)
+    out = torch.empty((1, 1, 16, 18, 32), dtype=torch.bfloat16, device=dev)
+    for label, env in (("default (skinny fc2, L2 prefetch)", {}), ("no prefetch", {"GTAV_PREFETCH": "0"}),
+                       ("skinny everywhere", {"GTAV_SKINNY": "all"}), ("tiled everywhere", {"GTAV_SKINNY": "0"}),
+                       ("no PDL", {"GTAV_PDL_OFF_NOTE": "set GTAV_PDL=0 before start to test"})):
+        if "GTAV_PDL_OFF_NOTE" in env:
+            continue
+        for k, v in env.items():
+            os.environ[k] = v
+        dit = DiT_models["DiT-S/2"]().to(dev).eval()
+        with torch.no_grad():
+            for b_ in dit.blocks:
+                for h_ in ("s", "t"):
+                    lin = getattr(b_, f"{h_}_adaLN_modulation")[-1]
+                    lin.weight.normal_(std=0.02)
+                    lin.bias.normal_(std=0.02)
+        dit.forward_last_frame(x, t)                      # packs, plans, fills conditioning + K/V cache
+        plan = dit._plan(1, 5)
+
+        def step():
+            N.check(lib.gtav_dit_last_frame(plan, x.data_ptr(), 0, rows[4:].data_ptr(), out.data_ptr(), st()), "last_frame")
+
+        def ctx():
+            N.check(lib.gtav_dit_context(plan, x.data_ptr(), 0, rows[:4].data_ptr(), st()), "context")
+
+        def dense():
+            N.check(lib.gtav_dit_backbone(plan, x.data_ptr(), 0, None, out.data_ptr() if False else dense_out.data_ptr(), st()), "backbone")
+        dense_out = torch.empty((1, 5, 16, 18, 32), dtype=torch.bfloat16, device=dev)
+        us = graph_time([step] * 8)
+        usc = graph_time([ctx] * 3)
+        usd = graph_time([dense] * 3)
+        report(f"engine: {label}", us, ms_last_frame_step=round(us / 1e3, 4), ms_context_pass=round(usc / 1e3, 4),
+               ms_dense_step=round(usd / 1e3, 4))
+        for k in env:
+            del os.environ[k]
+        del dit
+
+
 def main():
+    if "--engine" in sys.argv:
+        engine_steps()
+        return
     n = 64
     report("noise_clamp 9216 elems (near-empty kernel: PDL chain floor)", graph_time([ddim_like] * n))
     report("ln_modulate 144 rows", graph_time([ln] * n))
