@@ -78,8 +78,9 @@ void carve(gtav_dit_plan_s* p, void* ws, size_t* total) {
     const size_t ctx_rows = static_cast<size_t>(p->B) * (p->T - 1) * e->tokens;
     p->kv_cache = c.take(static_cast<size_t>(e->cfg.depth) * ctx_rows * 2 * D);
     const int m_last = p->B * e->tokens;
-    p->sk_ws = reinterpret_cast<float*>(c.take(p->B <= 3 ? skinny_workspace_bytes(m_last) / sizeof(bf16) : 0));
-    p->sk_counters = reinterpret_cast<int*>(c.take(256));
+    size_t ws_bytes = p->B <= 3 ? skinny_workspace_bytes(m_last) : 0;
+    p->sk_ws = reinterpret_cast<float*>(c.take(ws_bytes / sizeof(bf16)));
+    p->sk_counters = reinterpret_cast<int*>(c.take(1024));      // 512 ints: 2 per row / column block
     *total = c.off;
 }
 
@@ -108,15 +109,13 @@ int build_shape(gtav_dit_plan_s* p, Shape* sh, int frames, bool allow_skinny) {
     rc |= gemm_prepare(&sh->g_patch, p->xa, 64, static_cast<const bf16*>(w.patch_w), 64, gp(p->h, D, w.patch_b, M, D, 64), EPI_BIAS);
     const int nh = 2 * h->cfg.depth;
     sh->g_qkv.resize(nh); sh->g_out.resize(nh); sh->g_fc1.resize(nh); sh->g_fc2.resize(nh);
-    // The split-K weight-streaming kernel wins where K is long and N short (fc2: 8.6 vs 17.7 us at M = 144, in-graph,
-    // B200); for the K = 1024 GEMMs the tiled kernel's direct epilogue beats the partial-sum exchange (6-8 vs 8-10 us).
-    // GTAV_SKINNY=all forces it everywhere it fits, GTAV_SKINNY=0 nowhere.
+    // Measured in the real step (B200, B = 1, scripts/bench_graph.py --engine): weight-streaming split-K kernel for all
+    // four GEMMs 1.55 ms per last-frame step, tiled kernel for the K = 1024 ones 1.69 ms, tiled everywhere 2.16 ms.
+    // GTAV_SKINNY=0 turns the weight-streaming kernel off (tiled GEMM everywhere: bit-identical to the dense window).
     const bool sk_ok = allow_skinny && skinny_enabled() && p->sk_ws != nullptr;
-    const char* skenv = getenv("GTAV_SKINNY");
-    const bool sk_all = skenv != nullptr && skenv[0] == 'a';
-    sh->sk[0] = sk_ok && sk_all && skinny_pick_splits(M, 3 * D, D) > 0;
-    sh->sk[1] = sk_ok && sk_all && skinny_pick_splits(M, D, D) > 0;
-    sh->sk[2] = sk_ok && sk_all && skinny_pick_splits(M, 4 * D, D) > 0;
+    sh->sk[0] = sk_ok && skinny_pick_splits(M, 3 * D, D) > 0;
+    sh->sk[1] = sk_ok && skinny_pick_splits(M, D, D) > 0;
+    sh->sk[2] = sk_ok && skinny_pick_splits(M, 4 * D, D) > 0;
     sh->sk[3] = sk_ok && skinny_pick_splits(M, D, 4 * D) > 0;
     if (sh->sk[0]) sh->s_qkv.resize(nh);
     if (sh->sk[1]) sh->s_out.resize(nh);
@@ -295,7 +294,7 @@ int gtav_dit_plan_create(gtav_dit_t h, int B, int T, int cond_rows, void* worksp
     if (rc == 0) rc = build_shape(p, &p->full, T, false);
     if (rc == 0 && T >= 2) rc = build_shape(p, &p->ctx, T - 1, false);
     if (rc == 0) rc = build_shape(p, &p->last, 1, true);
-    if (rc == 0 && cudaMemset(p->sk_counters, 0, 512) != cudaSuccess) { set_error("dit_plan_create: clearing the split-K counters failed"); rc = -2; }
+    if (rc == 0 && cudaMemset(p->sk_counters, 0, 2048) != cudaSuccess) { set_error("dit_plan_create: clearing the split-K counters failed"); rc = -2; }
     if (rc) { delete p; return rc < 0 ? rc : -1; }
     *out = p;
     return 0;

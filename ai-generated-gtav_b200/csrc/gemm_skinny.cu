@@ -230,7 +230,9 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 16; ++i) __stcg(mine + static_cast<size_t>(c + i) * 128 + row, __uint_as_float(v[i]));
             }
-            __threadfence();
+            // release: partial stores ordered before the arrival below (fence + CTA barrier + relaxed atomic); the
+            // acq_rel fence is lighter than __threadfence()'s sequentially-consistent one
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
             epi_bar_sync();
             int* arrive = p.counters + 2 * rb;
             if (threadIdx.x == 128) {

@@ -123,8 +123,8 @@ def engine_steps():
     t = torch.tensor([[15, 15, 15, 15, 500]], device=dev)
     rows = torch.arange(5, dtype=torch.int32, device=dev)
     out = torch.empty((1, 1, 16, 18, 32), dtype=torch.bfloat16, device=dev)
-    for label, env in (("default (skinny fc2, L2 prefetch)", {}), ("no prefetch", {"GTAV_PREFETCH": "0"}),
-                       ("skinny everywhere", {"GTAV_SKINNY": "all"}), ("tiled everywhere", {"GTAV_SKINNY": "0"}),
+    for label, env in (("default (weight-streaming GEMM, L2 prefetch)", {}), ("no prefetch", {"GTAV_PREFETCH": "0"}),
+                       ("tiled GEMM everywhere", {"GTAV_SKINNY": "0"}),
                        ("no PDL", {"GTAV_PDL_OFF_NOTE": "set GTAV_PDL=0 before start to test"})):
         if "GTAV_PDL_OFF_NOTE" in env:
             continue

@@ -8,7 +8,7 @@ STAGES=${STAGES:-"tests smoke bench ncu"}
 for st in $STAGES; do
 case $st in
 tests) TAILN=30 run t_all python -m pytest tests -m gpu -q -s --no-header -p no:cacheprovider ;;
-tests_k) TAILN=8 run t_kernels python -m pytest tests/test_kernels_gpu.py -m gpu -q --no-header -p no:cacheprovider -k "skinny or temporal" ;;
+tests_k) TAILN=8 run t_kernels python -m pytest tests/test_kernels_gpu.py -m gpu -q --no-header -p no:cacheprovider -k "skinny or temporal or frame" ;;
 smoke) TAILN=5 run smoke python -c "import __graft_entry__ as g; g.smoke()" ;;
 bench) TAILN=5 run bench python bench.py ;;
 bench_dense) TAILN=5 run bench_dense python bench.py --algorithm dense --steps 1 --warmup 3 --no-cpu-baseline ;;

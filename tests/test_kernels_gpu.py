@@ -355,3 +355,4 @@ def test_temporal_attention_last_frame_matches_dense(lib):
     ref = dense.view(B, T, P, D)[:, T - 1].reshape(B * P, D)
     err = float((out.float() - ref.float()).abs().max())
     assert err <= 2 ** -7 * float(ref.float().abs().max()), err
+
