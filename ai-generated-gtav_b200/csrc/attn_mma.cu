@@ -8,194 +8,19 @@
 // mma.sync m16n8k16 tiles (flash-style: scores stay in registers, online softmax across key
 // blocks, P rounded to bf16 before P@V like the reference's fused SDPA backends).  q/k are rotated
 // in fp32 and rounded to bf16 once, as apply_rotary_emb does (rotary_embedding_torch.py:46-73).
-#include "common.cuh"
-#include "kernels.h"
+#include "attn_seq.cuh"
 
 namespace gtav {
-
-static constexpr int HD = 64;          // head dim
-static constexpr int SROW = HD + 8;    // smem row stride (bf16): 144 B keeps ldmatrix / fragment loads conflict-free
-
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_ptr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(smem_u32(smem_ptr)));
-}
-// rotate the adjacent pair packed in `u` by (cos, sin) and re-round to bf16
-__device__ __forceinline__ uint32_t rotate_pair(uint32_t u, float2 cs) {
-    const float2 x = unpack_bf16x2(u);
-    return pack_bf16x2(x.x * cs.x - x.y * cs.y, x.y * cs.x + x.x * cs.y);
-}
 
 // grid: (SEQ / (WARPS*16), heads, groups).  qkv rows of one group are consecutive.
 template <int SEQ, int KB, int WARPS, int ROT_PAIRS>
 __global__ void __launch_bounds__(WARPS * 32)
 attn_seq_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, const float2* __restrict__ rot) {
-    static_assert(SEQ % KB == 0 && KB % 16 == 0 && SEQ % (WARPS * 16) == 0, "tiling");
     __shared__ __align__(16) bf16 sK[KB * SROW];
     __shared__ __align__(16) bf16 sV[KB * SROW];
     pdl_trigger();
     pdl_wait();
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, tig = lane & 3;
-    const int head = blockIdx.y;
-    const int ld = 3 * heads * HD;
-    const size_t row_base = static_cast<size_t>(blockIdx.z) * SEQ;
-    const bf16* qbase = qkv + row_base * ld + head * HD;
-    const bf16* kbase = qbase + heads * HD;
-    const bf16* vbase = kbase + heads * HD;
-
-    // ---- Q fragments (16 rows x 64 dims per warp): raw loads first, rotary applied once the K/V loads of the
-    // first key block are in flight too (one global round trip for everything the block needs) ------------------
-    const int q0 = (blockIdx.x * WARPS + warp) * 16;        // first query row of this warp (within the group)
-    uint32_t qf[4][4];
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            const int r = q0 + g + (h & 1) * 8;
-            const int c = ks * 16 + 2 * tig + (h >> 1) * 8;
-            qf[ks][h] = *reinterpret_cast<const uint32_t*>(qbase + static_cast<size_t>(r) * ld + c);
-        }
-    }
-
-    float o[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
-    float m_run[2] = {-INFINITY, -INFINITY};
-    float l_run[2] = {0.f, 0.f};
-    const float sl2 = 0.125f * 1.4426950408889634f;          // 1/sqrt(64) * log2(e)
-    constexpr int STAGE_ITERS = (KB * 8) / (WARPS * 32);
-    static_assert((KB * 8) % (WARPS * 32) == 0, "staging loop must divide evenly");
-
-    for (int kb0 = 0; kb0 < SEQ; kb0 += KB) {
-        if (kb0 > 0) __syncthreads();                        // previous block fully consumed
-        // ---- stage K (rotated) and V for keys [kb0, kb0+KB): all loads issued before any is consumed ----------
-        uint4 kraw[STAGE_ITERS], vraw[STAGE_ITERS];
-#pragma unroll
-        for (int it = 0; it < STAGE_ITERS; ++it) {
-            const int i = threadIdx.x + it * WARPS * 32;
-            const int r = i >> 3, c8 = (i & 7) * 8;
-            const size_t goff = static_cast<size_t>(kb0 + r) * ld + c8;
-            kraw[it] = *reinterpret_cast<const uint4*>(kbase + goff);
-            vraw[it] = *reinterpret_cast<const uint4*>(vbase + goff);
-        }
-        if (kb0 == 0) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const int r = q0 + g + (h & 1) * 8;
-                    const int pr = (ks * 16 + 2 * tig + (h >> 1) * 8) >> 1;
-                    if (pr < ROT_PAIRS) qf[ks][h] = rotate_pair(qf[ks][h], rot[r * ROT_PAIRS + pr]);
-                }
-            }
-        }
-#pragma unroll
-        for (int it = 0; it < STAGE_ITERS; ++it) {
-            const int i = threadIdx.x + it * WARPS * 32;
-            const int r = i >> 3, c8 = (i & 7) * 8;
-            uint32_t kw[4] = {kraw[it].x, kraw[it].y, kraw[it].z, kraw[it].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int pr = (c8 >> 1) + j;
-                if (pr < ROT_PAIRS) kw[j] = rotate_pair(kw[j], rot[(kb0 + r) * ROT_PAIRS + pr]);
-            }
-            *reinterpret_cast<uint4*>(&sK[r * SROW + c8]) = make_uint4(kw[0], kw[1], kw[2], kw[3]);
-            *reinterpret_cast<uint4*>(&sV[r * SROW + c8]) = vraw[it];
-        }
-        __syncthreads();
-
-        // ---- S = Q K^T for this key block ------------------------------------------------------
-        float sc[KB / 8][4];
-#pragma unroll
-        for (int nt = 0; nt < KB / 8; ++nt) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) sc[nt][j] = 0.f;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                const bf16* kp = &sK[(nt * 8 + g) * SROW + ks * 16 + 2 * tig];
-                mma_bf16_16816(sc[nt], qf[ks], *reinterpret_cast<const uint32_t*>(kp),
-                               *reinterpret_cast<const uint32_t*>(kp + 8));
-            }
-        }
-        // ---- online softmax (rows g and g+8 of the warp's 16) ----------------------------------
-        float bm[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-        for (int nt = 0; nt < KB / 8; ++nt) {
-            bm[0] = fmaxf(bm[0], fmaxf(sc[nt][0], sc[nt][1]));
-            bm[1] = fmaxf(bm[1], fmaxf(sc[nt][2], sc[nt][3]));
-        }
-        float alpha[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            bm[h] = fmaxf(bm[h], __shfl_xor_sync(0xffffffffu, bm[h], 1));
-            bm[h] = fmaxf(bm[h], __shfl_xor_sync(0xffffffffu, bm[h], 2));
-            const float m_new = fmaxf(m_run[h], bm[h]);
-            alpha[h] = exp2f((m_run[h] - m_new) * sl2);
-            m_run[h] = m_new;
-            l_run[h] *= alpha[h];
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            o[i][0] *= alpha[0]; o[i][1] *= alpha[0];
-            o[i][2] *= alpha[1]; o[i][3] *= alpha[1];
-        }
-        const float mo0 = m_run[0] * sl2, mo1 = m_run[1] * sl2;
-#pragma unroll
-        for (int nt = 0; nt < KB / 8; ++nt) {
-            sc[nt][0] = exp2f(sc[nt][0] * sl2 - mo0);
-            sc[nt][1] = exp2f(sc[nt][1] * sl2 - mo0);
-            sc[nt][2] = exp2f(sc[nt][2] * sl2 - mo1);
-            sc[nt][3] = exp2f(sc[nt][3] * sl2 - mo1);
-            l_run[0] += sc[nt][0] + sc[nt][1];
-            l_run[1] += sc[nt][2] + sc[nt][3];
-        }
-        // ---- O += P V ---------------------------------------------------------------------------
-#pragma unroll
-        for (int j = 0; j < KB / 16; ++j) {
-            uint32_t pf[4];
-            pf[0] = pack_bf16x2(sc[2 * j][0], sc[2 * j][1]);
-            pf[1] = pack_bf16x2(sc[2 * j][2], sc[2 * j][3]);
-            pf[2] = pack_bf16x2(sc[2 * j + 1][0], sc[2 * j + 1][1]);
-            pf[3] = pack_bf16x2(sc[2 * j + 1][2], sc[2 * j + 1][3]);
-#pragma unroll
-            for (int dn = 0; dn < 8; dn += 2) {
-                // four 8x8 blocks of V: keys j*16 + {0..7, 8..15} x dims dn*8 + {0..7, 8..15}
-                const int mat = lane >> 3, r = lane & 7;
-                uint32_t vf[4];
-                ldmatrix_x4_trans(vf, &sV[(j * 16 + (mat & 1) * 8 + r) * SROW + (dn + (mat >> 1)) * 8]);
-                mma_bf16_16816(o[dn], pf, vf[0], vf[1]);
-                mma_bf16_16816(o[dn + 1], pf, vf[2], vf[3]);
-            }
-        }
-    }
-    // ---- normalise and store ----------------------------------------------------------------------
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 1);
-        l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 2);
-        l_run[h] = 1.0f / l_run[h];
-    }
-    const int ldo = heads * HD;
-    bf16* obase = out + row_base * ldo + head * HD;
-#pragma unroll
-    for (int dn = 0; dn < 8; ++dn) {
-        const int c = dn * 8 + 2 * tig;
-        *reinterpret_cast<uint32_t*>(obase + static_cast<size_t>(q0 + g) * ldo + c) =
-            pack_bf16x2(o[dn][0] * l_run[0], o[dn][1] * l_run[0]);
-        *reinterpret_cast<uint32_t*>(obase + static_cast<size_t>(q0 + g + 8) * ldo + c) =
-            pack_bf16x2(o[dn][2] * l_run[1], o[dn][3] * l_run[1]);
-    }
+    attn_seq_body<SEQ, KB, WARPS, ROT_PAIRS, false>(qkv, out, heads, rot, sK, sV, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, 0);
 }
 
 int launch_attention_seq(const bf16* qkv, bf16* out, int groups, int seq, int heads, const float2* rot, int rot_pairs,

@@ -40,8 +40,15 @@ struct gtav_dit_plan_s {
     // workspace slices
     bf16 *xa, *h, *hn, *qkv, *att, *mlp, *yfin, *temb, *aemb, *h1, *cact, *mod;
     bf16* kv_cache;          // [depth][B*(T-1)*tokens][2*hidden]: rotated K and V of the context frames per temporal layer
-    float* sk_ws;            // split-K partial sums of the weight-streaming GEMM
+    float* sk_ws;            // split-K partial sums of the weight-streaming GEMM / of the persistent step kernel
     int* sk_counters;
+    // persistent last-frame step kernel (B == 1): per-half descriptors (device), counters, LayerNorm partials
+    MegaHalfDev* mega_halves;
+    unsigned* mega_sync;
+    float2* mega_stats;
+    int* zero_row;
+    MegaParams mega;         // launch parameters of the step kernel (last_row / trace filled per launch)
+    bool use_mega;
     GemmOp g_t0, g_t2, g_ada;
     Shape full, ctx, last;   // all T frames / the T-1 context frames / the last frame only
 };
@@ -81,6 +88,12 @@ void carve(gtav_dit_plan_s* p, void* ws, size_t* total) {
     size_t ws_bytes = p->B <= 3 ? skinny_workspace_bytes(m_last) : 0;
     p->sk_ws = reinterpret_cast<float*>(c.take(ws_bytes / sizeof(bf16)));
     p->sk_counters = reinterpret_cast<int*>(c.take(1024));      // 512 ints: 2 per row / column block
+    if (p->B == 1) {
+        p->mega_halves = reinterpret_cast<MegaHalfDev*>(c.take(static_cast<size_t>(2 * e->cfg.depth) * sizeof(MegaHalfDev) / sizeof(bf16)));
+        p->mega_sync = reinterpret_cast<unsigned*>(c.take(mega_sync_bytes() / sizeof(bf16)));
+        p->mega_stats = reinterpret_cast<float2*>(c.take(mega_stats_bytes() / sizeof(bf16)));
+        p->zero_row = reinterpret_cast<int*>(c.take(64));
+    }
     *total = c.off;
 }
 
@@ -94,6 +107,57 @@ GemmParams gp(bf16* out, int ldo, const void* bias, int M, int N, int K) {
 bool skinny_enabled() {
     const char* e = getenv("GTAV_SKINNY");
     return !(e != nullptr && e[0] == '0');
+}
+
+// The persistent step kernel is opt-in (GTAV_MEGA=1): parity-green, but measured slower than the PDL-chained kernels
+// (profiles/r01/step_kernel_trace_v2.txt: ~69 us vs ~46 us per half-block; its L2-mediated split-K exchange and grid
+// barriers cost what the kernel boundaries did).
+bool mega_enabled() {
+    const char* e = getenv("GTAV_MEGA");
+    return e != nullptr && e[0] == '1';
+}
+
+// Device-side descriptors of the persistent last-frame step kernel (B == 1): one weight tensor map per GEMM.
+int build_mega(gtav_dit_plan_s* p) {
+    const gtav_dit_s* h = p->eng;
+    const int nh = 2 * h->cfg.depth, D = h->cfg.hidden;
+    std::vector<MegaHalfDev> host(nh);
+    for (int i = 0; i < nh; ++i) {
+        const gtav_dit_half& hw = h->halves[i];
+        const void* w[4] = {hw.qkv_w, hw.out_w, hw.fc1_w, hw.fc2_w};
+        for (int k = 0; k < 4; ++k) {
+            const int rc = mega_make_weight_map(&host[i].tm[k], static_cast<const bf16*>(w[k]), k);
+            if (rc) return rc;
+        }
+        host[i].out_b = static_cast<const bf16*>(hw.out_b);
+        host[i].fc1_b = static_cast<const bf16*>(hw.fc1_b);
+        host[i].fc2_b = static_cast<const bf16*>(hw.fc2_b);
+        host[i].mod_off = i * 6 * D;
+        host[i].pad_ = 0;
+    }
+    if (cudaMemcpy(p->mega_halves, host.data(), host.size() * sizeof(MegaHalfDev), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemset(p->mega_sync, 0, mega_sync_bytes()) != cudaSuccess || cudaMemset(p->zero_row, 0, 64) != cudaSuccess) {
+        set_error("dit_plan_create: uploading the step-kernel descriptors failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return -2;
+    }
+    const gtav_dit_config& c = h->cfg;
+    MegaParams& mp = p->mega;
+    mp = MegaParams{};
+    mp.halves = p->mega_halves; mp.n_halves = nh;
+    mp.h = p->h; mp.qkv = p->qkv; mp.att = p->att; mp.mlp = p->mlp;
+    mp.mod = p->mod; mp.mod_ld = h->mod_width;
+    mp.ws = p->sk_ws; mp.stats = p->mega_stats; mp.sync = p->mega_sync;
+    mp.kv_cache = p->kv_cache;
+    mp.cache_layer_stride = static_cast<size_t>(p->B) * (p->T - 1) * h->tokens * 2 * D;
+    mp.ctx_frames = p->T - 1;
+    mp.rot_s = reinterpret_cast<const float2*>(h->w.rot_spatial);
+    mp.rot_t = reinterpret_cast<const float2*>(h->w.rot_temporal);
+    mp.grid = mega_grid();
+    (void)c;
+    const int rc = mega_make_act_maps(&mp);
+    if (rc) return rc;
+    p->use_mega = true;
+    return 0;
 }
 
 // Descriptors of the backbone GEMMs for `frames` frames per rollout.  allow_skinny: use the weight-streaming
@@ -169,7 +233,15 @@ int run_backbone(gtav_dit_plan_s* p, const Shape* sh, int mode, const void* x, i
     const float2* rot_s = reinterpret_cast<const float2*>(e->w.rot_spatial);
     const float2* rot_t = reinterpret_cast<const float2*>(e->w.rot_temporal);
     const size_t cache_layer = static_cast<size_t>(p->B) * (p->T - 1) * S * 2 * D;
-    for (int i = 0; i < 2 * c.depth; ++i) {
+    const bool mega = mode == MODE_LAST && p->use_mega;
+    if (mega) {
+        // all 2*depth half-blocks in one persistent kernel (dit_step_mega.cu)
+        MegaParams mp = p->mega;
+        mp.last_row = frame_row != nullptr ? frame_row : p->zero_row;
+        if (const char* tr = getenv("GTAV_MEGA_TRACE")) mp.trace = reinterpret_cast<long long*>(strtoull(tr, nullptr, 0));
+        if ((rc = mega_run(mp, stream))) return rc;
+    }
+    for (int i = 0; i < 2 * c.depth && !mega; ++i) {
         const int off = i * 6 * D;          // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
         if ((rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, off, off + D, frame_row, S, stream))) return rc;
         if (sh->sk[0]) rc = skinny_run(&sh->s_qkv[i], stream);
@@ -295,6 +367,7 @@ int gtav_dit_plan_create(gtav_dit_t h, int B, int T, int cond_rows, void* worksp
     if (rc == 0 && T >= 2) rc = build_shape(p, &p->ctx, T - 1, false);
     if (rc == 0) rc = build_shape(p, &p->last, 1, true);
     if (rc == 0 && cudaMemset(p->sk_counters, 0, 2048) != cudaSuccess) { set_error("dit_plan_create: clearing the split-K counters failed"); rc = -2; }
+    if (rc == 0 && B == 1 && mega_enabled()) rc = build_mega(p);
     if (rc) { delete p; return rc < 0 ? rc : -1; }
     *out = p;
     return 0;

@@ -105,6 +105,40 @@ int skinny_prepare(SkinnyOp* op, const bf16* A, int lda, const bf16* W, int ldw,
                    int* counters, int splits_override = 0);
 int skinny_run(const SkinnyOp* op, cudaStream_t stream);
 
+// ---------------------------------------------------------------- persistent last-frame step (dit_step_mega.cu)
+// The 2*depth half-blocks of a last-frame DiT step at B = 1 (144 rows) as one persistent kernel: see the file header.
+struct alignas(64) MegaHalfDev {
+    CUtensorMap tm[4];                  // weight maps: to_qkv, to_out, fc1, fc2 (3-D view, 128-row x chunks boxes)
+    const bf16 *out_b, *fc1_b, *fc2_b;
+    int mod_off;                        // column of this half's (shift, scale, gate) x 2 inside a modulation row
+    int pad_;
+};
+struct MegaParams {
+    CUtensorMap tm_att, tm_mlp;         // A operands of to_out / fc2: [144, D] and [144, 4D], boxes of 144 rows x chunks
+    const MegaHalfDev* halves;          // device array [n_halves]
+    int n_halves;
+    bf16 *h, *qkv, *att, *mlp;          // [144, D], [144, 3D], [144, D], [144, 4D]
+    const bf16* mod;                    // conditioning table, row = *last_row
+    int mod_ld;
+    const int* last_row;
+    float* ws;                          // fp32 split-K partials, mega_ws_bytes()
+    float2* stats;                      // LayerNorm (mean, M2) partials [144][8]
+    unsigned* sync;                     // zero-initialised counters, mega_sync_bytes()
+    const bf16* kv_cache;               // [layer][ctx_frames*144][2D]
+    size_t cache_layer_stride;          // elements between temporal layers
+    int ctx_frames;
+    const float2 *rot_s, *rot_t;
+    int grid;
+    long long* trace;                   // optional [grid][2][32] globaltimer stamps (profiling aid), normally null
+};
+size_t mega_sync_bytes();
+size_t mega_stats_bytes();
+size_t mega_ws_bytes();
+int mega_grid();
+int mega_make_weight_map(CUtensorMap* out, const bf16* W, int kind);
+int mega_make_act_maps(MegaParams* p);     // tm_att / tm_mlp from p->att / p->mlp
+int mega_run(const MegaParams& p, cudaStream_t stream);
+
 // ---------------------------------------------------------------- row kernels (norm_mod.cu)
 // out = bf16( LN(x) * bf16(1 + bf16(scale + 1e-6)) + shift ), LN without affine, eps 1e-6.
 // shift/scale of row r live at mod + frame_row[r / rows_per_frame] * mod_ld + {shift_off, scale_off}.

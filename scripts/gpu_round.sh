@@ -8,6 +8,7 @@ STAGES=${STAGES:-"tests smoke bench ncu"}
 for st in $STAGES; do
 case $st in
 tests) TAILN=30 run t_all python -m pytest tests -m gpu -q -s --no-header -p no:cacheprovider ;;
+tests_mega) TAILN=25 run t_mega python -m pytest tests/test_model_gpu.py -m gpu -q -s --no-header -p no:cacheprovider -k "last_frame or step_kernel" ;;
 tests_k) TAILN=8 run t_kernels python -m pytest tests/test_kernels_gpu.py -m gpu -q --no-header -p no:cacheprovider -k "skinny or temporal or frame" ;;
 smoke) TAILN=5 run smoke python -c "import __graft_entry__ as g; g.smoke()" ;;
 bench) TAILN=5 run bench python bench.py ;;

@@ -78,26 +78,54 @@ def test_dit_forward_bf16_input_and_replan():
         check(v, rp.dit_forward(sd, cfg, x.float(), t, None, rp.BF16), TOL_BF16, f"bf16 input B={B} T={T}")
 
 
-@pytest.mark.parametrize("skinny", ["0", "1"])
-def test_dit_last_frame_split_equals_dense(monkeypatch, skinny):
-    """Context pass + last-frame-only pass (the sampler's frame cache) == the last frame of the dense forward.
-    With the tiled GEMM on both sides (GTAV_SKINNY=0) the two paths run the same arithmetic per row; with the
-    weight-streaming GEMM only the fp32 summation order inside the K splits differs."""
+LAST_FRAME_MODES = {
+    # name: (GTAV_SKINNY, GTAV_MEGA, max-abs bound vs the dense window)
+    "tiled": ("0", "0", 0.0),        # same kernels, same arithmetic per row: bit-identical
+    "skinny": ("1", "0", 2e-2),      # weight-streaming GEMM: fp32 summation order inside the K splits differs
+    "step_kernel": ("1", "1", 3e-2), # persistent step kernel (B = 1): + LayerNorm statistics merged from 8 partials
+}
+
+
+@pytest.mark.parametrize("mode", list(LAST_FRAME_MODES))
+def test_dit_last_frame_split_equals_dense(monkeypatch, mode):
+    """Context pass + last-frame-only pass (the sampler's frame cache) == the last frame of the dense forward."""
     from gtav_b200.model.dit import DiT
+    skinny, mega, bound = LAST_FRAME_MODES[mode]
     monkeypatch.setenv("GTAV_SKINNY", skinny)
+    monkeypatch.setenv("GTAV_MEGA", mega)
     sd = make_dit_state(DiTConfig(depth=2), seed=0)
     model = DiT(depth=2)
     model.load_state_dict(sd, strict=True)
     model = model.cuda().eval()
-    for B, T, seed, actions in ((1, 5, 81, True), (2, 3, 82, False), (1, 2, 83, True), (4, 5, 84, True)):
+    for B, T, seed, actions in ((1, 5, 81, True), (2, 3, 82, False), (1, 2, 83, True), (4, 5, 84, True), (1, 1, 85, False)):
         x = seeded_randn((B, T, 16, 18, 32), seed).cuda()
         t = torch.randint(0, 1000, (B, T), generator=torch.Generator().manual_seed(seed)).cuda()
         a = w_key_actions(B, T).cuda() if actions else None
         dense = model(x, t, a)[:, -1:]
         split = model.forward_last_frame(x, t, a)
+        again = model.forward_last_frame(x, t, a)
         err = float((dense.float() - split.float()).abs().max())
-        print(f"skinny={skinny} B={B} T={T}: last-frame split vs dense max-abs {err:.5f} equal={torch.equal(dense, split)}")
-        assert err <= (0.0 if skinny == "0" else 2e-2), err
+        print(f"{mode} B={B} T={T}: last-frame split vs dense max-abs {err:.5f} equal={torch.equal(dense, split)}")
+        assert err <= bound, err
+        assert torch.equal(split, again), "last-frame pass is not deterministic"
+
+
+@pytest.mark.parametrize("mega", ["1", "0"])
+def test_step_kernel_full_depth_vs_reference_golden(golden, monkeypatch, mega):
+    """The persistent step kernel on the real 16-block DiT (B = 1, T = 5): last frame of the v-prediction against the
+    unmodified reference's fp32 output, same tolerance as the dense forward."""
+    monkeypatch.setenv("GTAV_MEGA", mega)
+    from gtav_b200.model.dit import DiT
+    c = CASES_DIT["d16_b1_t5_act"]
+    sd = make_dit_state(DiTConfig(depth=16), seed=0)
+    model = DiT(depth=16)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    x = seeded_randn((1, 5, 16, 18, 32), c["seed"])
+    t = torch.tensor(c["t"]).reshape(1, 5)
+    a = w_key_actions(1, 5)
+    v_last = model.forward_last_frame(x.cuda(), t.cuda(), a.cuda())
+    check(v_last, golden("dit_forward")["d16_b1_t5_act.v"][:, -1:], TOL_FP32, f"last-frame pass (step kernel={mega}), depth 16, vs reference fp32 golden")
 
 
 def test_dit_rejects_cpu_and_bad_shapes():
