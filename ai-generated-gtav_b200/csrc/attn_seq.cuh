@@ -44,7 +44,9 @@ __device__ __forceinline__ uint4 attn_ld128(const bf16* p) {
 // qkv with ld.global.cg (the buffer was written by other CTAs of the SAME kernel - persistent step kernel).
 // PRESTAGED (needs SEQ == KB): the caller has already put the rotated K, V and the rotated WARPS*16 query rows of this
 // item (sQ, row stride SROW) into shared memory and synchronised; the body only computes.
-template <int SEQ, int KB, int WARPS, int ROT_PAIRS, bool COHERENT, bool PRESTAGED = false>
+// TILED_OUT (SEQ == 144 only): `out` is the pre-tiled activation image [head = 64-column chunk][144 rows][64] with
+// the 128-byte swizzle of an UMMA K-major operand (16-byte chunk index ^ (row & 7)) instead of a row-major matrix.
+template <int SEQ, int KB, int WARPS, int ROT_PAIRS, bool COHERENT, bool PRESTAGED = false, bool TILED_OUT = false>
 __device__ __forceinline__ void attn_seq_body(const bf16* qkv, bf16* out, int heads, const float2* __restrict__ rot, bf16* sK,
                                               bf16* sV, int qblock, int head, int group, int tid, int bar_id,
                                               const bf16* sQ = nullptr) {
@@ -200,10 +202,17 @@ __device__ __forceinline__ void attn_seq_body(const bf16* qkv, bf16* out, int he
 #pragma unroll
     for (int dn = 0; dn < 8; ++dn) {
         const int c = dn * 8 + 2 * tig;
-        *reinterpret_cast<uint32_t*>(obase + static_cast<size_t>(q0 + g) * ldo + c) =
-            pack_bf16x2(o[dn][0] * l_run[0], o[dn][1] * l_run[0]);
-        *reinterpret_cast<uint32_t*>(obase + static_cast<size_t>(q0 + g + 8) * ldo + c) =
-            pack_bf16x2(o[dn][2] * l_run[1], o[dn][3] * l_run[1]);
+        const uint32_t lo = pack_bf16x2(o[dn][0] * l_run[0], o[dn][1] * l_run[0]);
+        const uint32_t hi = pack_bf16x2(o[dn][2] * l_run[1], o[dn][3] * l_run[1]);
+        if (TILED_OUT) {
+            uint8_t* tile = reinterpret_cast<uint8_t*>(out) + static_cast<size_t>(head) * (SEQ * 128);
+            const int r0 = q0 + g, r1 = q0 + g + 8;
+            *reinterpret_cast<uint32_t*>(tile + r0 * 128 + ((dn ^ (r0 & 7)) << 4) + tig * 4) = lo;
+            *reinterpret_cast<uint32_t*>(tile + r1 * 128 + ((dn ^ (r1 & 7)) << 4) + tig * 4) = hi;
+        } else {
+            *reinterpret_cast<uint32_t*>(obase + static_cast<size_t>(q0 + g) * ldo + c) = lo;
+            *reinterpret_cast<uint32_t*>(obase + static_cast<size_t>(q0 + g + 8) * ldo + c) = hi;
+        }
     }
 }
 

@@ -45,7 +45,7 @@ struct gtav_dit_plan_s {
     // persistent last-frame step kernel (B == 1): per-half descriptors (device), counters, LayerNorm partials
     MegaHalfDev* mega_halves;
     unsigned* mega_sync;
-    float2* mega_stats;
+    uint8_t* mega_buf[6];    // hn_t, att_t, mlp_t, qkv_h, ws_out, ws_fc2
     int* zero_row;
     MegaParams mega;         // launch parameters of the step kernel (last_row / trace filled per launch)
     bool use_mega;
@@ -91,7 +91,7 @@ void carve(gtav_dit_plan_s* p, void* ws, size_t* total) {
     if (p->B == 1) {
         p->mega_halves = reinterpret_cast<MegaHalfDev*>(c.take(static_cast<size_t>(2 * e->cfg.depth) * sizeof(MegaHalfDev) / sizeof(bf16)));
         p->mega_sync = reinterpret_cast<unsigned*>(c.take(mega_sync_bytes() / sizeof(bf16)));
-        p->mega_stats = reinterpret_cast<float2*>(c.take(mega_stats_bytes() / sizeof(bf16)));
+        for (int i = 0; i < 6; ++i) p->mega_buf[i] = reinterpret_cast<uint8_t*>(c.take(mega_buffer_bytes(i) / sizeof(bf16)));
         p->zero_row = reinterpret_cast<int*>(c.take(64));
     }
     *total = c.off;
@@ -140,22 +140,21 @@ int build_mega(gtav_dit_plan_s* p) {
         set_error("dit_plan_create: uploading the step-kernel descriptors failed: %s", cudaGetErrorString(cudaGetLastError()));
         return -2;
     }
-    const gtav_dit_config& c = h->cfg;
     MegaParams& mp = p->mega;
     mp = MegaParams{};
     mp.halves = p->mega_halves; mp.n_halves = nh;
-    mp.h = p->h; mp.qkv = p->qkv; mp.att = p->att; mp.mlp = p->mlp;
+    mp.h = p->h;
+    mp.hn_t = p->mega_buf[0]; mp.att_t = p->mega_buf[1]; mp.mlp_t = p->mega_buf[2];
+    mp.qkv_h = reinterpret_cast<bf16*>(p->mega_buf[3]);
+    mp.ws_out = reinterpret_cast<float*>(p->mega_buf[4]); mp.ws_fc2 = reinterpret_cast<float*>(p->mega_buf[5]);
     mp.mod = p->mod; mp.mod_ld = h->mod_width;
-    mp.ws = p->sk_ws; mp.stats = p->mega_stats; mp.sync = p->mega_sync;
+    mp.sync = p->mega_sync;
     mp.kv_cache = p->kv_cache;
     mp.cache_layer_stride = static_cast<size_t>(p->B) * (p->T - 1) * h->tokens * 2 * D;
     mp.ctx_frames = p->T - 1;
     mp.rot_s = reinterpret_cast<const float2*>(h->w.rot_spatial);
     mp.rot_t = reinterpret_cast<const float2*>(h->w.rot_temporal);
     mp.grid = mega_grid();
-    (void)c;
-    const int rc = mega_make_act_maps(&mp);
-    if (rc) return rc;
     p->use_mega = true;
     return 0;
 }

@@ -17,8 +17,8 @@
 //   * partial accumulators go to an fp32 workspace (L2), the S CTAs of a row block meet on a
 //     counter, and each reduces + runs the fused epilogue for its 1/S share of the tokens, summing
 //     the partials in split order (deterministic).
-// Warp roles (256 threads): 0 = W producer, 1 = A producer, 2 = TMEM allocator + MMA issuer,
-// 4-7 = epilogue (one TMEM lane quadrant each).
+// Warp roles (256 threads): 0 = W producer, 1 = A producer, 2 = TMEM allocator + MMA issuer, 4-7 = L2 prefetch of
+// the next GEMM's weights; all 8 warps drain the accumulator (one TMEM lane quadrant each, half of the columns) and reduce.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -53,7 +53,12 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 
 // One output element: column n (this thread's weight row), token `tok`, fp32 pre-bias value `acc`.
 template <int EPI>
@@ -111,6 +116,33 @@ template <int EPI, int S>
 __device__ __forceinline__ void skinny_reduce(const GemmParams& g, const float* part, int total, int lo, int hi, int wid, int lane,
                                               int n0) {
     const float* base = part + 4 * lane;
+    if (S <= 4) {
+        // few splits: a warp's tokens (at most 5 per 144-token tile share) are loaded together, so the whole reduce costs
+        // one L2 round trip instead of one per token
+        constexpr int IT = 5;
+#pragma unroll 1
+        for (int t0 = lo + wid; t0 < hi; t0 += 8 * IT) {
+            float4 v[IT][S];
+#pragma unroll
+            for (int it = 0; it < IT; ++it) {
+                const int tok = t0 + 8 * it;
+#pragma unroll
+                for (int s2 = 0; s2 < S; ++s2)
+                    if (tok < hi) v[it][s2] = __ldcg(reinterpret_cast<const float4*>(base + (static_cast<size_t>(s2) * total + tok) * 128));
+            }
+#pragma unroll
+            for (int it = 0; it < IT; ++it) {
+                const int tok = t0 + 8 * it;
+                if (tok < hi) {
+                    float4 acc = v[it][0];
+#pragma unroll
+                    for (int s2 = 1; s2 < S; ++s2) { acc.x += v[it][s2].x; acc.y += v[it][s2].y; acc.z += v[it][s2].z; acc.w += v[it][s2].w; }
+                    skinny_store4<EPI>(g, tok, n0 + 4 * lane, acc);
+                }
+            }
+        }
+        return;
+    }
 #pragma unroll 1
     for (int tok = lo + wid; tok < hi; tok += 8) {
         float4 v[S];
@@ -196,22 +228,22 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             umma_commit(bar_acc);
         }
         pdl_wait();
+    } else if (warp == 3) {
+        pdl_wait();
     } else if (warp >= 4) {
         // idle until the accumulator is ready: pull the NEXT GEMM's weights into L2 meanwhile
         l2_prefetch_share(p.g.prefetch, p.g.prefetch_bytes, (blockIdx.x * 4 + (warp - 4)) * 32 + lane, gridDim.x * 128);
         pdl_wait();
-        const GemmParams& g = p.g;
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const int n = rb * 128 + row;
-        const int total = tiles * SK_NT;
-        float bias_n = 0.f;
-        if (EPI != EPI_STORE) bias_n = __bfloat162float(g.bias[n]);
-        mbar_wait(bar_acc, 0);
-        tcgen05_fence_after();
-        if (threadIdx.x == 128) SK_STAMP(4);                                   // accumulator complete
-        const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         if (S == 1) {
+            const GemmParams& g = p.g;
+            const int q = warp & 3;
+            const int n = rb * 128 + q * 32 + lane;
+            const int total = tiles * SK_NT;
+            float bias_n = 0.f;
+            if (EPI != EPI_STORE) bias_n = __bfloat162float(g.bias[n]);
+            mbar_wait(bar_acc, 0);
+            tcgen05_fence_after();
+            const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
             for (int c = 0; c < total; c += 16) {
                 uint32_t v[16];
@@ -220,38 +252,51 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 16; ++i) skinny_store<EPI>(g, c + i, n, __uint_as_float(v[i]), bias_n);
             }
-        } else {
-            float* mine = p.ws + static_cast<size_t>(blockIdx.x) * total * 128;
+        }
+    }
+    if (S > 1) {
+        // ---- accumulator -> fp32 partial tile ws[cta][token][128 weight rows], drained by ALL 8 warps: warp w reads the
+        // TMEM lane quadrant w % 4, warps 4-7 the first half of the token columns, warps 0-3 (whose producer / MMA roles
+        // are over) the second half
+        const int total = tiles * SK_NT, half = total / 2;
+        const int q = warp & 3, row = q * 32 + lane;
+        mbar_wait(bar_acc, 0);
+        tcgen05_fence_after();
+        if (threadIdx.x == 128) SK_STAMP(4);                                   // accumulator complete
+        const int c0 = warp < 4 ? half : 0;
+        const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0;
+        float* mine = p.ws + static_cast<size_t>(blockIdx.x) * total * 128 + static_cast<size_t>(c0) * 128 + row;
 #pragma unroll 1
-            for (int c = 0; c < total; c += 16) {
-                uint32_t v[16];
-                tmem_ld_32x16(tlane + c, v);
-                tmem_ld_wait();
+        for (int c = 0; c < half; c += 24) {                                   // half = 72 * tiles
+            uint32_t v[3][8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) __stcg(mine + static_cast<size_t>(c + i) * 128 + row, __uint_as_float(v[i]));
-            }
-            // release: partial stores ordered before the arrival below (fence + CTA barrier + relaxed atomic); the
-            // acq_rel fence is lighter than __threadfence()'s sequentially-consistent one
-            asm volatile("fence.acq_rel.gpu;" ::: "memory");
-            epi_bar_sync();
+            for (int j = 0; j < 3; ++j) tmem_ld_32x8(tlane + c + 8 * j, v[j]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) __stcg(mine + static_cast<size_t>(c + 8 * j + i) * 128, __uint_as_float(v[j][i]));
+        }
+        // release: partial stores ordered before the arrival below (fence + CTA barrier + relaxed atomic); the
+        // acq_rel fence is lighter than __threadfence()'s sequentially-consistent one
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 128) {
             int* arrive = p.counters + 2 * rb;
-            if (threadIdx.x == 128) {
-                SK_STAMP(5);                                                   // partials written + fenced
-                atomicAdd(arrive, 1);
-                uint32_t spins = 0;
-                while (ld_acquire_gpu(arrive) < S) {
-                    __nanosleep(64);
-                    if (++spins > (1u << 24)) {
-                        printf("gtav: split-K rendezvous timed out (block %d)\n", blockIdx.x);
-                        __trap();
-                    }
+            SK_STAMP(5);                                                       // partials written + fenced
+            atomicAdd(arrive, 1);
+            uint32_t spins = 0;
+            while (ld_acquire_gpu(arrive) < S) {
+                __nanosleep(64);
+                if (++spins > (1u << 24)) {
+                    printf("gtav: split-K rendezvous timed out (block %d)\n", blockIdx.x);
+                    __trap();
                 }
             }
         }
     }
     if (S > 1) {
-        // all 8 warps reduce: warps 0-3 get here as soon as their producer / MMA roles are done and wait for the
-        // epilogue warps, which arrive once the rendezvous of the row block has completed
+        // all 8 warps reduce once the rendezvous of the row block has completed
         __syncthreads();
         if (threadIdx.x == 128) SK_STAMP(6);                                   // rendezvous passed
         const GemmParams& g = p.g;

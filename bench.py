@@ -139,6 +139,19 @@ def launches_per_rollout(wl, algorithm, depth=16, enc=6, dec=12):
     return gen * per_frame + vae_enc + vae_dec * ((wl["B"] * wl["total"] + 31) // 32)
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r*/roofline_traffic.json)."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", "roofline_traffic.json")), reverse=True):
+        try:
+            d = json.load(open(path)).get(kernel)
+        except Exception:
+            d = None
+        if d:
+            return d["traffic_bytes_per_launch"]
+    return None
+
+
 def _hot_weights(dit):
     """Packed bf16 weights in _pack order: per half qkv_w, out_w, out_b, fc1_w, fc1_b, fc2_w, fc2_b."""
     dit._pack()
@@ -197,7 +210,7 @@ def gemm_roofline(dit, B, pk):
     ms = _time_passes(one_pass)                         # GEMM time of one DiT step (128 launches)
     tf = DIT_GEMM_GFLOP * B / ms                        # GFLOP / ms = TFLOP/s
     return dict(bound="tensor", achieved=round(tf, 1), peak=pk["tf"], unit="TFLOP/s", frac=round(tf / pk["tf"], 4),
-                traffic=None, kernel="gemm_bf16_kernel (tcgen05, 128 launches per dense DiT step)",
+                traffic=measured_traffic("gemm_bf16_kernel"), kernel="gemm_bf16_kernel (tcgen05, 128 launches per dense DiT step)",
                 gemm_ms_per_dit_step=round(ms, 4), peak_source=f"{pk['src']} sustained bf16")
 
 
@@ -233,7 +246,8 @@ def skinny_roofline(dit, B, pk):
     per_half = sum(2 * (n * k + M * k + M * n) for _, _, _, n, k, _ in shapes)          # bf16 bytes: W + A + out
     gb = len(halves) * per_half / 1e9
     gbs = gb / (ms / 1e3)
-    return dict(bound="hbm", achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s", frac=round(gbs / pk["hbm"], 4), traffic=None,
+    return dict(bound="hbm", achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s", frac=round(gbs / pk["hbm"], 4),
+                traffic=measured_traffic("gemm_skinny_kernel"),
                 kernel="gemm_skinny_kernel (tcgen05 weight-streaming GEMM, 128 launches per last-frame DiT step)",
                 algorithmic_mb_per_launch=round(gb * 1e3 / (4 * len(halves)), 3), us_per_launch=round(ms * 1e3 / (4 * len(halves)), 3),
                 gemm_ms_per_last_frame_step=round(ms, 4), peak_source=f"{pk['src']} HBM copy bandwidth")

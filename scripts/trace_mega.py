@@ -5,6 +5,7 @@ import sys
 
 import torch
 
+os.environ["GTAV_MEGA"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gtav_b200.model.dit import DiT_models
 
@@ -29,13 +30,9 @@ for _ in range(3):
 torch.cuda.synchronize()
 del os.environ["GTAV_MEGA_TRACE"]
 tr = trace.cpu()
-names = {0: "half start"}
-for k, nm in enumerate(("qkv", "out", "fc1", "fc2")):
-    for j, st in enumerate(("start", "A filled", "acc done", "partials stored", "rendezvous", "reduced")):
-        names[1 + 7 * k + j] = f"{nm}: {st}"
-names.update({7: "barrier after qkv", 29: "attention done", 30: "barrier after attention", 14: "barrier after out", 21: "barrier after fc1",
-              28: "barrier after fc2"})
-order = [0, 1, 2, 3, 4, 5, 6, 7, 29, 30, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28]
+names = ["half start", "qkv gemm done", "barrier", "attention done", "barrier", "out gemm done", "barrier", "row phase (h += gate*out, LN2) done",
+         "barrier", "fc1 gemm done", "barrier", "fc2 gemm done", "barrier", "row phase (h += gate*fc2, LN1) done", "barrier"]
+order = list(range(15))
 for hsel, label in ((0, "half 2 (spatial)"), (1, "half 3 (temporal)")):
     t0 = tr[:, hsel, 0].min()
     print(f"# {label}: ns since the first CTA entered the half; min / median / max over the CTAs that stamped")
@@ -44,4 +41,4 @@ for hsel, label in ((0, "half 2 (spatial)"), (1, "half 3 (temporal)")):
         col = col[col > 0] - t0
         if col.numel() == 0:
             continue
-        print(f"  {names[sl]:<26} n={col.numel():3d}  {int(col.min()):7d} {int(col.median()):7d} {int(col.max()):7d}")
+        print(f"  {names[sl]:<44} n={col.numel():3d}  {int(col.min()):7d} {int(col.median()):7d} {int(col.max()):7d}")
