@@ -5,18 +5,18 @@
 // with the surrounding elementwise ops (bias, GELU/SiLU, adaLN gate, residual) fused as epilogues that
 // round to bf16 exactly where the reference's autocast graph does.
 //
-// Structure (one 128 x BN output tile per CTA, 224 threads):
-//   warp 0   : TMA producer of A - one cp.async.bulk.tensor per stage: KC consecutive 64-wide K chunks of 128 rows
-//   warp 6   : TMA producer of W - the same for BN weight rows; runs ahead of the previous kernel (PDL): weights
+// Structure (persistent CTAs over 128 x BN output tiles, double-buffered TMEM accumulator, 224 threads):
+//   warps 0,7: TMA producers of A - a stage is KC = 2 consecutive 64-wide K chunks of 128 rows, one box per thread
+//   warps 6,8: TMA producers of W - the same for BN weight rows; they run ahead of the previous kernel (PDL): weights
 //              do not depend on it
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1)
 //   warps 2-5: epilogue      - tcgen05.ld 32x32b from their TMEM lane quadrant, fused math, 16-byte stores
 // smem full/empty mbarrier ring between the producers and the issuer; tcgen05.commit frees slots and signals
 // the epilogue.  Out-of-range rows / columns / K are zero-filled by TMA and masked in the epilogue.
-// Why two producers and multi-chunk boxes: measured on B200 (scripts/probe_tma*.cu, profiles/r01), one warp gets a
-// bulk-tensor copy accepted only every ~0.4 us whatever its size and an SM runs two at a time, so a stage made of
-// two 16 KB boxes issued by one thread caps a CTA at ~45 GB/s (5x short of what a 128x128 tile needs); two warps
-// issuing 32 KB boxes (KC = 2, via a [64 | rows | K/64] 3-D view) reach ~160 GB/s per SM.
+// Why four producer threads: measured on B200 (scripts/probe_tma*.cu, scripts/probe_mcast.cu, profiles/r01), one
+// thread gets a bulk copy accepted only every ~0.4 us whatever its size, so a stage issued by one thread caps a CTA
+// at ~45 GB/s (5x short of what a 128x128 tile needs) and two threads with 32 KB boxes at ~160 GB/s; copies from
+// different threads proceed in parallel, and a 128 x 256 tile at full tensor rate needs ~175 GB/s.
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -29,7 +29,7 @@ namespace gtav {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;                 // one 128-byte-swizzled chunk
-static constexpr int GEMM_THREADS = 224;
+static constexpr int GEMM_THREADS = 288;
 
 template <int BN, int STAGES, int KC>
 struct GemmSmem {
@@ -38,9 +38,13 @@ struct GemmSmem {
     static constexpr int A_BYTES = KC * A_CHUNK;           // per stage
     static constexpr int B_BYTES = KC * B_CHUNK;
     static constexpr int BAR_OFF = STAGES * (A_BYTES + B_BYTES);
-    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;   // +1024: manual alignment slack
+    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16 + 1024;   // +1024: manual alignment slack
 };
 
+// Persistent: CTA b works on output tiles b, b + gridDim.x, ... (n fastest, so neighbouring CTAs share the A rows in
+// L2).  The accumulator is double-buffered in TMEM (2 x BN columns): while the epilogue warps drain tile i, the MMA
+// issuer already accumulates tile i + 1, and the two TMA producers run ahead across tile boundaries - the per-tile
+// prologue / epilogue (as long as a K = 1024 mainloop) leaves the critical path.
 template <int BN, int STAGES, int KC, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -51,13 +55,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* sB = smem + STAGES * L::A_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* accum_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* tfull_bar = empty_bar + STAGES;      // [2] accumulator complete
+    uint64_t* tempty_bar = tfull_bar + 2;          // [2] accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_blk = blockIdx.x;
-    const int m_blk = blockIdx.y;
+    const int n_tiles_n = (p.N + BN - 1) / BN;
+    const int n_tiles = n_tiles_n * ((p.M + BM - 1) / BM);
     const int num_ks = (p.K + KC * BK - 1) / (KC * BK);      // pipeline stages along K (KC chunks each)
 
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tmA);
@@ -65,14 +70,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < STAGES; ++s) {
-                mbar_init(&full_bar[s], 2);           // one arrive.expect_tx per producer
+                mbar_init(&full_bar[s], 2 * KC);      // one arrive.expect_tx per producer thread
                 mbar_init(&empty_bar[s], 1);
             }
-            mbar_init(accum_bar, 1);
+            for (int a = 0; a < 2; ++a) {
+                mbar_init(&tfull_bar[a], 1);
+                mbar_init(&tempty_bar[a], 4);         // one arrival per epilogue warp
+            }
             fence_barrier_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, BN);
+        tmem_alloc(tmem_slot, 2 * BN);
         tmem_relinquish();
     }
     tcgen05_fence_before();
@@ -81,78 +89,101 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
     pdl_trigger();                                // the next kernel may start its own set-up now
 
-    if (warp == 0) {
+    if (warp == 0 || warp == 7) {
+        // A producers: thread j (warp 0 -> j = 0, warp 7 -> j = 1) loads K chunk j of every stage
+        const int j = warp == 0 ? 0 : 1;
         pdl_wait();                               // A is the previous kernel's output
-        if (lane == 0) {
-            for (int ks = 0; ks < num_ks; ++ks) {
-                const int s = ks % STAGES;
-                mbar_wait(&empty_bar[s], ((ks / STAGES) & 1) ^ 1);
-                mbar_arrive_expect_tx(&full_bar[s], L::A_BYTES);
-                if (KC == 1) tma_load_2d(sA + s * L::A_BYTES, &tmA, &full_bar[s], ks * BK, m_blk * BM);
-                else tma_load_3d(sA + s * L::A_BYTES, &tmA, &full_bar[s], 0, m_blk * BM, ks * KC);
+        if (lane == 0 && j < KC) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m_blk = tile / n_tiles_n;
+                for (int ks = 0; ks < num_ks; ++ks, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[s], L::A_CHUNK);
+                    tma_load_2d(sA + s * L::A_BYTES + j * L::A_CHUNK, &tmA, &full_bar[s], (ks * KC + j) * BK, m_blk * BM);
+                }
             }
         }
-    } else if (warp == 6) {
-        if (lane == 0) {
-            // weights are never written by the kernel before us: stream them without waiting for it
-            for (int ks = 0; ks < num_ks; ++ks) {
-                const int s = ks % STAGES;
-                mbar_wait(&empty_bar[s], ((ks / STAGES) & 1) ^ 1);
-                mbar_arrive_expect_tx(&full_bar[s], L::B_BYTES);
-                if (KC == 1) tma_load_2d(sB + s * L::B_BYTES, &tmB, &full_bar[s], ks * BK, n_blk * BN);
-                else tma_load_3d(sB + s * L::B_BYTES, &tmB, &full_bar[s], 0, n_blk * BN, ks * KC);
+    } else if (warp == 6 || warp == 8) {
+        // W producers, the same split; weights are never written by the kernel before us: stream them without waiting
+        const int j = warp == 6 ? 0 : 1;
+        if (lane == 0 && j < KC) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int n_blk = tile % n_tiles_n;
+                for (int ks = 0; ks < num_ks; ++ks, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[s], L::B_CHUNK);
+                    tma_load_2d(sB + s * L::B_BYTES + j * L::B_CHUNK, &tmB, &full_bar[s], (ks * KC + j) * BK, n_blk * BN);
+                }
             }
         }
         pdl_wait();
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-            for (int ks = 0; ks < num_ks; ++ks) {
-                const int s = ks % STAGES;
-                mbar_wait(&full_bar[s], (ks / STAGES) & 1);
+            int it = 0, local = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+                const int acc = local & 1;
+                mbar_wait(&tempty_bar[acc], ((local >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
                 tcgen05_fence_after();
+                const uint32_t tmem_acc = tmem_base + acc * BN;
+                for (int ks = 0; ks < num_ks; ++ks, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                    tcgen05_fence_after();
 #pragma unroll
-                for (int c = 0; c < KC; ++c) {
-                    const uint64_t da = umma_desc_sw128(smem_u32(sA + s * L::A_BYTES + c * L::A_CHUNK));
-                    const uint64_t db = umma_desc_sw128(smem_u32(sB + s * L::B_BYTES + c * L::B_CHUNK));
+                    for (int c = 0; c < KC; ++c) {
+                        const uint64_t da = umma_desc_sw128(smem_u32(sA + s * L::A_BYTES + c * L::A_CHUNK));
+                        const uint64_t db = umma_desc_sw128(smem_u32(sB + s * L::B_BYTES + c * L::B_CHUNK));
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // +32 bytes (16 bf16) along K inside the 128-byte swizzle row: +2 in 16-byte units
-                        umma_bf16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (ks | c | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // +32 bytes (16 bf16) along K inside the 128-byte swizzle row: +2 in 16-byte units
+                            umma_bf16_ss(tmem_acc, da + 2 * k, db + 2 * k, idesc, (ks | c | k) != 0 ? 1u : 0u);
+                        }
                     }
+                    umma_commit(&empty_bar[s]);       // slot reusable once these MMAs have read it
                 }
-                umma_commit(&empty_bar[s]);       // slot reusable once these MMAs have read it
+                umma_commit(&tfull_bar[acc]);         // accumulator complete
             }
-            umma_commit(accum_bar);               // accumulator complete
         }
         pdl_wait();
     } else {
-        // idle until the accumulator is ready: pull the NEXT GEMM's weights into L2 meanwhile
-        l2_prefetch_share(p.prefetch, p.prefetch_bytes, ((blockIdx.y * gridDim.x + blockIdx.x) * 4 + (warp - 2)) * 32 + lane,
-                          gridDim.x * gridDim.y * 128);
+        // idle until the first accumulator is ready: pull the NEXT GEMM's weights into L2 meanwhile
+        l2_prefetch_share(p.prefetch, p.prefetch_bytes, (blockIdx.x * 4 + (warp - 2)) * 32 + lane, gridDim.x * 128);
         pdl_wait();                               // bias / gate / residual may come from the previous kernel
         const int q = warp & 3;                   // TMEM lane quadrant this warp may read
-        const int row = m_blk * BM + q * 32 + lane;
-        const bf16* gate_row = nullptr;
-        if (EPI == EPI_BIAS_GATE_RES && row < p.M) {
-            int f = row / p.rows_per_frame;
-            if (p.frame_row != nullptr) f = p.frame_row[f];
-            gate_row = p.gate + static_cast<size_t>(f) * p.gate_ld;
-        }
-        mbar_wait(accum_bar, 0);
-        tcgen05_fence_after();
+        int local = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+            const int m_blk = tile / n_tiles_n, n_blk = tile % n_tiles_n;
+            const int acc = local & 1;
+            const int row = m_blk * BM + q * 32 + lane;
+            const bf16* gate_row = nullptr;
+            if (EPI == EPI_BIAS_GATE_RES && row < p.M) {
+                int f = row / p.rows_per_frame;
+                if (p.frame_row != nullptr) f = p.frame_row[f];
+                gate_row = p.gate + static_cast<size_t>(f) * p.gate_ld;
+            }
+            mbar_wait(&tfull_bar[acc], (local >> 1) & 1);
+            tcgen05_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t acc[32];
-            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, acc);
-            tmem_ld_wait();
-            const int col0 = n_blk * BN + c * 32;
-            if (row < p.M && col0 < p.N) epilogue_chunk<EPI>(p, row, col0, acc, gate_row);
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
+                tmem_ld_wait();
+                const int col0 = n_blk * BN + c * 32;
+                if (row < p.M && col0 < p.N) epilogue_chunk<EPI>(p, row, col0, v, gate_row);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);     // this warp's quadrant of the accumulator is free
         }
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, BN);
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -265,9 +296,18 @@ int gemm_prepare(GemmOp* op, const bf16* A, int lda, const bf16* W, int ldw, con
     const int m_tiles = (p.M + BM - 1) / BM;
     int bn = bn_override;
     if (bn == 0) {
-        if (p.N <= 64) bn = 64;
-        else if ((p.N % 256) == 0 && m_tiles * (p.N / 256) >= num_sms()) bn = 256;
-        else bn = 128;
+        // cost of one tile per K = 16 step, in cycles: the larger of the MMA (61 / 68 / 130 cycles at BN = 64 / 128 / 256,
+        // scripts/probe_umma_rate.cu) and the operand ingest at the ~160 GB/s per SM two TMA producer warps reach
+        // (71 / 95 / 142); times the number of rounds the persistent CTAs need.  Ties go to the wider tile.
+        const int cand[3] = {256, 128, 64};
+        const double cost[3] = {142.0, 95.0, 71.0};
+        double best = 1e30;
+        for (int i = 0; i < 3; ++i) {
+            if (cand[i] > 64 && p.N <= cand[i] / 2) continue;               // mostly padding
+            const int tiles = m_tiles * ((p.N + cand[i] - 1) / cand[i]);
+            const double c = static_cast<double>((tiles + num_sms() - 1) / num_sms()) * cost[i];
+            if (c < best - 1e-9) { best = c; bn = cand[i]; }
+        }
     }
     if (bn != 64 && bn != 128 && bn != 256) {
         set_error("gemm: tile width %d not in {64,128,256}", bn);
@@ -276,16 +316,12 @@ int gemm_prepare(GemmOp* op, const bf16* A, int lda, const bf16* W, int ldw, con
     op->p = p;
     op->bn = bn;
     op->epi = epi;
-    // two 64-wide K chunks per TMA instruction whenever K allows the [64 | rows | K/64] view
-    op->kc = (p.K % BK == 0 && p.K >= 2 * BK) ? 2 : 1;
-    if (op->kc == 1) {
-        int rc = make_tmap(&op->tmA, A, p.M, p.K, lda, BM);
-        if (rc) return rc;
-        return make_tmap(&op->tmB, W, p.N, p.K, ldw, bn);
-    }
-    int rc = make_tmap_3d(&op->tmA, A, p.M, p.K, lda, BM, op->kc);
+    // two 64-wide K chunks per pipeline stage (one per producer thread) unless K is a single chunk
+    op->kc = p.K > BK ? 2 : 1;
+    // one 2-D box (rows x 64) per K chunk and producer thread, whatever the stage depth
+    int rc = make_tmap(&op->tmA, A, p.M, p.K, lda, BM);
     if (rc) return rc;
-    return make_tmap_3d(&op->tmB, W, p.N, p.K, ldw, bn, op->kc);
+    return make_tmap(&op->tmB, W, p.N, p.K, ldw, bn);
 }
 
 template <int BN, int STAGES, int KC, int EPI>
@@ -297,7 +333,8 @@ static int launch_one(const GemmOp* op, cudaStream_t stream) {
         GTAV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         configured = true;
     }
-    dim3 grid((op->p.N + BN - 1) / BN, (op->p.M + BM - 1) / BM, 1);
+    const int tiles = ((op->p.N + BN - 1) / BN) * ((op->p.M + BM - 1) / BM);
+    dim3 grid(tiles < num_sms() ? tiles : num_sms(), 1, 1);
     GTAV_CUDA_OK(launch_k(kern, grid, dim3(GEMM_THREADS), L::TOTAL, stream, op->tmA, op->tmB, op->p));
     return 0;
 }

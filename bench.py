@@ -42,6 +42,9 @@ WORKLOADS = {
                desc="action-conditioned (W key), B=8 rollouts, 32 frames (4 prompt), 100 noise steps"),
     "c1": dict(B=1, total=8, n_prompt=4, steps=10, actions=False,
                desc="generate.py CPU case: B=1, 8 frames (4 prompt), 10 noise steps"),
+    # 64 rollouts in total, sharded over the ranks (strong scaling): B = 64 / world per GPU
+    "c5": dict(B=64, total=32, n_prompt=4, steps=100, actions=True, shard=True,
+               desc="64 independent action-conditioned rollouts batch-sharded over the GPUs, 32 frames (4 prompt), 100 noise steps"),
 }
 DIT_STEP_GFLOP = 589.09          # per sample, 5-frame window
 DIT_GEMM_GFLOP = 579.8           # the four per-half GEMMs only
@@ -316,10 +319,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-algorithm comparison leg")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    strong = bool(wl.get("shard"))
+    if strong:                                   # fixed total work: this rank's share of the rollouts (shard.py: r % world)
+        from gtav_b200.shard import shard_rollouts
+        wl["B"] = len(shard_rollouts(wl["B"], rank, world))
 
     if args.impl == "reference":
         run_reference_arm(args, wl, rank, world)
@@ -421,7 +428,8 @@ def main():
             roof = gemm_roofline(dit, B, pk)
             algo = "dense (every step recomputes the whole 5-frame window, like the reference)"
         line = dict(metric=METRIC, value=round(value, 3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=round(ms_total / args.steps, 2), higher_is_better=True, scaling="weak", vs_baseline=None,
+                    ms_per_step=round(ms_total / args.steps, 2), higher_is_better=True, scaling="strong" if strong else "weak",
+                    vs_baseline=None,
                     dtype="bf16", data="synthetic",
                     config=dict(workload=wl["desc"], rollouts_per_gpu=B, frames=total, prompt_frames=n_prompt,
                                 noise_steps=wl["steps"], dit_evals_per_rollout=gen * (wl["steps"] + 1),
