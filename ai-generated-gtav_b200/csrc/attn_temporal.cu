@@ -6,6 +6,7 @@
 // arange(T), theta 1e4).  T x T scores with T <= 5 are far too small for tensor cores: this kernel
 // is L2/HBM-bound (reads the 3*D-wide qkv rows once, writes D), one warp per problem, each lane owns
 // one rotary pair (2 of the 64 head dims), dot products reduced with shuffles.
+#include "attn_temporal_core.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -96,45 +97,14 @@ attn_temporal_last_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, 
     const int b = static_cast<int>(wg / (static_cast<long>(heads) * P));
     const int D = heads * 64;
 
-    float2 k[TC + 1], v[TC + 1];
-#pragma unroll
-    for (int t = 0; t < TC; ++t) {
-        const size_t row = (static_cast<size_t>(b) * TC + t) * P + pos;
-        const bf16* c = kv_cache + row * (2 * D) + head * 64 + 2 * lane;
-        k[t] = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(c));
-        v[t] = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(c + D));
-    }
     const size_t qrow = static_cast<size_t>(b) * P + pos;
     const bf16* base = qkv + qrow * (3 * D) + head * 64 + 2 * lane;
-    const float2 cs = rot[TC * 32 + lane];
+    const bf16* cache = kv_cache + (static_cast<size_t>(b) * TC * P + pos) * (2 * D) + head * 64 + 2 * lane;
     const float2 qx = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(base));
     const float2 kx = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(base + D));
-    const float2 q = make_float2(bf16_round(qx.x * cs.x - qx.y * cs.y), bf16_round(qx.y * cs.x + qx.x * cs.y));
-    k[TC] = make_float2(bf16_round(kx.x * cs.x - kx.y * cs.y), bf16_round(kx.y * cs.x + kx.x * cs.y));
-    v[TC] = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(base + 2 * D));
-
-    float s[TC + 1];
-    float m = -INFINITY;
-#pragma unroll
-    for (int j = 0; j <= TC; ++j) {
-        s[j] = warp_sum(q.x * k[j].x + q.y * k[j].y) * 0.125f;
-        m = fmaxf(m, s[j]);
-    }
-    float l = 0.f;
-#pragma unroll
-    for (int j = 0; j <= TC; ++j) {
-        s[j] = __expf(s[j] - m);
-        l += s[j];
-    }
-    const float inv = 1.0f / l;
-    float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j <= TC; ++j) {
-        const float p = bf16_round(s[j] * inv);
-        acc.x += p * v[j].x;
-        acc.y += p * v[j].y;
-    }
-    *reinterpret_cast<uint32_t*>(out + qrow * D + head * 64 + 2 * lane) = pack_bf16x2(acc.x, acc.y);
+    const float2 vx = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(base + 2 * D));
+    *reinterpret_cast<uint32_t*>(out + qrow * D + head * 64 + 2 * lane) =
+        temporal_last_core<TC>(qx, kx, vx, cache, static_cast<size_t>(P) * 2 * D, D, rot[TC * 32 + lane]);
 }
 
 int launch_attention_temporal_last(const bf16* qkv, bf16* out, int B, int ctx_frames, int positions, int heads,

@@ -30,6 +30,9 @@ struct Shape {
     // weight-streaming variants (last-frame shape only); sk[kind] says whether kind uses them
     std::vector<SkinnyOp> s_qkv, s_out, s_fc1, s_fc2;
     bool sk[4] = {false, false, false, false};
+    // row-wise kernels folded into the weight-streaming GEMMs' reduce (gemm_skinny.cu): the LayerNorm + modulate after
+    // to_out / fc2, the last-frame temporal attention after the temporal half's to_qkv
+    bool fuse_ln = false, fuse_tattn = false;
 };
 
 enum BackboneMode { MODE_FULL = 0, MODE_CONTEXT = 1, MODE_LAST = 2 };
@@ -112,6 +115,12 @@ bool skinny_enabled() {
 // The persistent step kernel is opt-in (GTAV_MEGA=1): parity-green, but measured slower than the PDL-chained kernels
 // (profiles/r01/step_kernel_trace_v2.txt: ~69 us vs ~46 us per half-block; its L2-mediated split-K exchange and grid
 // barriers cost what the kernel boundaries did).
+// GTAV_FUSE=0 keeps LayerNorm and temporal attention as kernels of their own (same results, bit for bit).
+bool fuse_enabled() {
+    const char* e = getenv("GTAV_FUSE");
+    return !(e != nullptr && e[0] == '0');
+}
+
 bool mega_enabled() {
     const char* e = getenv("GTAV_MEGA");
     return e != nullptr && e[0] == '1';
@@ -184,6 +193,9 @@ int build_shape(gtav_dit_plan_s* p, Shape* sh, int frames, bool allow_skinny) {
     if (sh->sk[1]) sh->s_out.resize(nh);
     if (sh->sk[2]) sh->s_fc1.resize(nh);
     if (sh->sk[3]) sh->s_fc2.resize(nh);
+    sh->fuse_ln = sh->sk[1] && sh->sk[3] && fuse_enabled();
+    sh->fuse_tattn = sh->sk[0] && fuse_enabled() && skinny_pick_splits(M, 3 * D, D) == 4 && p->T - 1 <= 7;
+    const size_t cache_layer = static_cast<size_t>(p->B) * (p->T - 1) * S * 2 * D;
     for (int i = 0; i < nh && rc == 0; ++i) {
         const gtav_dit_half& hw = h->halves[i];
         const bf16* modl = p->mod + static_cast<size_t>(i) * 6 * D;
@@ -202,13 +214,29 @@ int build_shape(gtav_dit_plan_s* p, Shape* sh, int frames, bool allow_skinny) {
             p1.prefetch = hw.fc2_w; p1.prefetch_bytes = 4 * DD;
             if (i + 1 < nh) { p2.prefetch = h->halves[i + 1].qkv_w; p2.prefetch_bytes = 3 * DD; }
         }
-        if (sh->sk[0]) rc |= skinny_prepare(&sh->s_qkv[i], p->hn, D, static_cast<const bf16*>(hw.qkv_w), D, pq, EPI_STORE, p->sk_ws, p->sk_counters);
+        // fused reduces: LN2 of this half after to_out, LN1 of the next half (or the final layer's norm) after fc2,
+        // temporal attention after the temporal half's to_qkv
+        SkinnyFuseParams f_out{}, f_fc2{}, f_qkv{};
+        f_out.mode = f_fc2.mode = SK_FUSE_LN;
+        f_out.ln_out = f_fc2.ln_out = p->hn;
+        f_out.ln_mod = f_fc2.ln_mod = p->mod;
+        f_out.ln_mod_ld = f_fc2.ln_mod_ld = W;
+        f_out.ln_shift_off = i * 6 * D + 3 * D; f_out.ln_scale_off = i * 6 * D + 4 * D;
+        f_fc2.ln_shift_off = (i + 1) * 6 * D; f_fc2.ln_scale_off = (i + 1) * 6 * D + D;      // i + 1 == nh: final layer
+        f_qkv.mode = SK_FUSE_TATTN;
+        f_qkv.kv_cache = p->kv_cache + static_cast<size_t>(i >> 1) * cache_layer;
+        f_qkv.rot = reinterpret_cast<const float2*>(w.rot_temporal);
+        f_qkv.ctx_frames = p->T - 1;
+        f_qkv.positions = S;
+        const bool ta = sh->fuse_tattn && (i & 1);
+        if (ta) { pq.out = p->att; pq.ldo = D; }
+        if (sh->sk[0]) rc |= skinny_prepare(&sh->s_qkv[i], p->hn, D, static_cast<const bf16*>(hw.qkv_w), D, pq, EPI_STORE, p->sk_ws, p->sk_counters, 0, ta ? &f_qkv : nullptr);
         else rc |= gemm_prepare(&sh->g_qkv[i], p->hn, D, static_cast<const bf16*>(hw.qkv_w), D, pq, EPI_STORE);
-        if (sh->sk[1]) rc |= skinny_prepare(&sh->s_out[i], p->att, D, static_cast<const bf16*>(hw.out_w), D, po, EPI_BIAS_GATE_RES, p->sk_ws, p->sk_counters);
+        if (sh->sk[1]) rc |= skinny_prepare(&sh->s_out[i], p->att, D, static_cast<const bf16*>(hw.out_w), D, po, EPI_BIAS_GATE_RES, p->sk_ws, p->sk_counters, 0, sh->fuse_ln ? &f_out : nullptr);
         else rc |= gemm_prepare(&sh->g_out[i], p->att, D, static_cast<const bf16*>(hw.out_w), D, po, EPI_BIAS_GATE_RES);
         if (sh->sk[2]) rc |= skinny_prepare(&sh->s_fc1[i], p->hn, D, static_cast<const bf16*>(hw.fc1_w), D, p1, EPI_BIAS_GELU_TANH, p->sk_ws, p->sk_counters);
         else rc |= gemm_prepare(&sh->g_fc1[i], p->hn, D, static_cast<const bf16*>(hw.fc1_w), D, p1, EPI_BIAS_GELU_TANH);
-        if (sh->sk[3]) rc |= skinny_prepare(&sh->s_fc2[i], p->mlp, 4 * D, static_cast<const bf16*>(hw.fc2_w), 4 * D, p2, EPI_BIAS_GATE_RES, p->sk_ws, p->sk_counters);
+        if (sh->sk[3]) rc |= skinny_prepare(&sh->s_fc2[i], p->mlp, 4 * D, static_cast<const bf16*>(hw.fc2_w), 4 * D, p2, EPI_BIAS_GATE_RES, p->sk_ws, p->sk_counters, 0, sh->fuse_ln ? &f_fc2 : nullptr);
         else rc |= gemm_prepare(&sh->g_fc2[i], p->mlp, 4 * D, static_cast<const bf16*>(hw.fc2_w), 4 * D, p2, EPI_BIAS_GATE_RES);
     }
     rc |= gemm_prepare(&sh->g_final, p->hn, D, static_cast<const bf16*>(w.final_w), D, gp(p->yfin, 64, w.final_b, M, h->out_feat, D), EPI_BIAS);
@@ -240,13 +268,16 @@ int run_backbone(gtav_dit_plan_s* p, const Shape* sh, int mode, const void* x, i
         if (const char* tr = getenv("GTAV_MEGA_TRACE")) mp.trace = reinterpret_cast<long long*>(strtoull(tr, nullptr, 0));
         if ((rc = mega_run(mp, stream))) return rc;
     }
+    bool hn_ready = false;                  // the previous fc2's reduce already wrote this half's LN1 output
     for (int i = 0; i < 2 * c.depth && !mega; ++i) {
         const int off = i * 6 * D;          // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
-        if ((rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, off, off + D, frame_row, S, stream))) return rc;
+        if (!hn_ready && (rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, off, off + D, frame_row, S, stream))) return rc;
         if (sh->sk[0]) rc = skinny_run(&sh->s_qkv[i], stream);
         else rc = gemm_run(&sh->g_qkv[i], stream);
         if (rc) return rc;
-        if ((i & 1) == 0) {
+        if (sh->s_qkv.size() && sh->sk[0] && sh->s_qkv[i].f.mode == SK_FUSE_TATTN) {
+            // temporal attention ran inside to_qkv's reduce
+        } else if ((i & 1) == 0) {
             rc = launch_attention_seq(p->qkv, p->att, F, S, c.heads, rot_s, 32, stream);
         } else {
             bf16* cache = p->kv_cache + static_cast<size_t>(i >> 1) * cache_layer;
@@ -264,7 +295,7 @@ int run_backbone(gtav_dit_plan_s* p, const Shape* sh, int mode, const void* x, i
             rc = gemm_run(&o, stream);
         }
         if (rc) return rc;
-        if ((rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, off + 3 * D, off + 4 * D, frame_row, S, stream))) return rc;
+        if (!sh->fuse_ln && (rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, off + 3 * D, off + 4 * D, frame_row, S, stream))) return rc;
         if (sh->sk[2]) rc = skinny_run(&sh->s_fc1[i], stream);
         else rc = gemm_run(&sh->g_fc1[i], stream);
         if (rc) return rc;
@@ -278,10 +309,11 @@ int run_backbone(gtav_dit_plan_s* p, const Shape* sh, int mode, const void* x, i
             rc = gemm_run(&o, stream);
         }
         if (rc) return rc;
+        hn_ready = sh->fuse_ln;
     }
     if (out == nullptr) return 0;
     const int foff = 2 * c.depth * 6 * D;   // final layer: shift, scale
-    if ((rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, foff, foff + D, frame_row, S, stream))) return rc;
+    if (!(hn_ready && !mega) && (rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, foff, foff + D, frame_row, S, stream))) return rc;
     if ((rc = gemm_run(&sh->g_final, stream))) return rc;
     return launch_dit_unpatchify(p->yfin, static_cast<bf16*>(out), F, c.in_channels, c.grid_h, c.grid_w, c.patch, stream);
 }

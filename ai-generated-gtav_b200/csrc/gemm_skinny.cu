@@ -19,8 +19,10 @@
 //     the partials in split order (deterministic).
 // Warp roles (256 threads): 0 = W producer, 1 = A producer, 2 = TMEM allocator + MMA issuer, 4-7 = L2 prefetch of
 // the next GEMM's weights; all 8 warps drain the accumulator (one TMEM lane quadrant each, half of the columns) and reduce.
+#include "attn_temporal_core.cuh"
 #include "common.cuh"
 #include "kernels.h"
+#include "ln_row.cuh"
 
 namespace gtav {
 
@@ -32,7 +34,9 @@ static constexpr int SK_SMEM_BUDGET = 200 * 1024;
 
 struct SkinnyParams {
     GemmParams g;
+    SkinnyFuseParams f;    // what the reduce produces besides / instead of the Linear's output (FUSE template parameter)
     int splits, chunks, tiles;
+    int gemm_ctas;         // (N/128) * splits; CTAs beyond that (fused modes) only take part in the per-token reduce
     float* ws;
     int* counters;
     long long* trace;      // optional [gridDim.x][8] globaltimer stamps (ns) of the phase boundaries; null in production
@@ -78,9 +82,10 @@ __device__ __forceinline__ void skinny_store(const GemmParams& g, int tok, int n
     g.out[static_cast<size_t>(tok) * g.ldo + n] = __float2bfloat16_rn(y);
 }
 
-// Four consecutive output columns n..n+3 of token `tok` (split-K reduce path: 8-byte vector accesses).
+// Four consecutive output columns n..n+3 of token `tok` (split-K reduce path: 8-byte vector accesses): the epilogue's
+// bf16 results, packed.
 template <int EPI>
-__device__ __forceinline__ void skinny_store4(const GemmParams& g, int tok, int n, float4 acc) {
+__device__ __forceinline__ uint2 skinny_epi4(const GemmParams& g, int tok, int n, float4 acc) {
     float y[4] = {acc.x, acc.y, acc.z, acc.w};
     if (EPI != EPI_STORE) {
         const uint2 bv = *reinterpret_cast<const uint2*>(g.bias + n);
@@ -106,7 +111,11 @@ __device__ __forceinline__ void skinny_store4(const GemmParams& g, int tok, int 
     uint2 o;
     o.x = pack_bf16x2(y[0], y[1]);
     o.y = pack_bf16x2(y[2], y[3]);
-    *reinterpret_cast<uint2*>(g.out + static_cast<size_t>(tok) * g.ldo + n) = o;
+    return o;
+}
+template <int EPI>
+__device__ __forceinline__ void skinny_store4(const GemmParams& g, int tok, int n, float4 acc) {
+    *reinterpret_cast<uint2*>(g.out + static_cast<size_t>(tok) * g.ldo + n) = skinny_epi4<EPI>(g, tok, n, acc);
 }
 
 // Sum the S partial tiles of this row block for tokens lo + wid, lo + wid + 8, ... (one warp per token, lane = 4
@@ -156,7 +165,100 @@ __device__ __forceinline__ void skinny_reduce(const GemmParams& g, const float* 
     }
 }
 
-template <int EPI>
+// ---- fused reduces: the CTAs meet on ALL row-block counters and every CTA then owns whole token rows (token
+// blockIdx.x, blockIdx.x + gridDim.x, ...), so that row-wise work that follows the Linear can run right here instead
+// of in another kernel of the latency-bound last-frame chain.
+//
+// SK_FUSE_LN (N = 1024, gated-residual epilogue: to_out and fc2 of reference model/dit.py:205-224): warp w sums the
+// partials of row block w, the new residual-stream row goes to g.out and, as bf16, to shared memory; warp 0 then
+// runs the NEXT LayerNorm + modulate on it with ln_rows_kernel's own code (same bits as the stand-alone kernel).
+template <int S>
+__device__ __forceinline__ void skinny_reduce_ln(const SkinnyParams& p, int total, int warp, int lane, uint8_t* srow) {
+    const GemmParams& g = p.g;
+    const SkinnyFuseParams& f = p.f;
+    const int n = warp * 128 + 4 * lane;
+    const float* base = p.ws + static_cast<size_t>(warp) * S * total * 128 + 4 * lane;
+#pragma unroll 1
+    for (int tok = blockIdx.x; tok < total; tok += gridDim.x) {
+        float4 v[S];
+#pragma unroll
+        for (int s2 = 0; s2 < S; ++s2) v[s2] = __ldcg(reinterpret_cast<const float4*>(base + (static_cast<size_t>(s2) * total + tok) * 128));
+        uint4 shu[4], scu[4];
+        if (warp == 0) {
+            int fr = tok / g.rows_per_frame;
+            if (g.frame_row != nullptr) fr = g.frame_row[fr];
+            const bf16* mrow = f.ln_mod + static_cast<size_t>(fr) * f.ln_mod_ld;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                shu[c] = *reinterpret_cast<const uint4*>(mrow + f.ln_shift_off + c * 256 + lane * 8);
+                scu[c] = *reinterpret_cast<const uint4*>(mrow + f.ln_scale_off + c * 256 + lane * 8);
+            }
+        }
+        float4 acc = v[0];
+#pragma unroll
+        for (int s2 = 1; s2 < S; ++s2) { acc.x += v[s2].x; acc.y += v[s2].y; acc.z += v[s2].z; acc.w += v[s2].w; }
+        const uint2 o = skinny_epi4<EPI_BIAS_GATE_RES>(g, tok, n, acc);
+        *reinterpret_cast<uint2*>(g.out + static_cast<size_t>(tok) * g.ldo + n) = o;
+        *reinterpret_cast<uint2*>(srow + n * 2) = o;
+        __syncthreads();
+        if (warp == 0) {
+            uint4 xu[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) xu[c] = *reinterpret_cast<const uint4*>(srow + (c * 256 + lane * 8) * 2);
+            float x[4][8];
+            float mean, rstd;
+            ln_row_stats<4>(xu, x, mean, rstd);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(f.ln_out + static_cast<size_t>(tok) * 1024 + c * 256 + lane * 8) =
+                    ln_modulate_slice(x[c], mean, rstd, shu[c], scu[c]);
+        }
+        __syncthreads();
+    }
+}
+
+// SK_FUSE_TATTN (N = 3072 = q | k | v of 16 heads, plain-store epilogue: to_qkv of the temporal half, reference
+// model/attention.py:41-66): warp w sums the partials of heads 2w and 2w + 1 (row blocks w, 8 + w, 16 + w), lane =
+// one rotary pair, and runs the last-frame temporal attention against the K/V cache with attn_temporal_last_kernel's
+// own code; g.out receives the ATTENTION output [tokens, 1024] (the q/k/v row itself is not needed afterwards).
+template <int S, int TC>
+__device__ __forceinline__ void skinny_reduce_tattn(const SkinnyParams& p, int total, int warp, int lane) {
+    const GemmParams& g = p.g;
+    const SkinnyFuseParams& f = p.f;
+    constexpr int D = 1024;
+    const int P = f.positions;
+    const float2 cs = f.rot[TC * 32 + lane];
+#pragma unroll 1
+    for (int tok = blockIdx.x; tok < total; tok += gridDim.x) {
+        const int b = tok / P, pos = tok - b * P;
+        float2 a[2][3][S];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+                const float* base = p.ws + (static_cast<size_t>(part * 8 + warp) * S * total + tok) * 128 + hh * 64 + 2 * lane;
+#pragma unroll
+                for (int s2 = 0; s2 < S; ++s2) a[hh][part][s2] = __ldcg(reinterpret_cast<const float2*>(base + static_cast<size_t>(s2) * total * 128));
+            }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            float2 qkv[3];
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+                float2 acc = a[hh][part][0];
+#pragma unroll
+                for (int s2 = 1; s2 < S; ++s2) { acc.x += a[hh][part][s2].x; acc.y += a[hh][part][s2].y; }
+                qkv[part] = make_float2(bf16_round(acc.x), bf16_round(acc.y));       // the Linear's bf16 output
+            }
+            const int head = 2 * warp + hh;
+            const bf16* cache = f.kv_cache + (static_cast<size_t>(b) * TC * P + pos) * (2 * D) + head * 64 + 2 * lane;
+            *reinterpret_cast<uint32_t*>(g.out + static_cast<size_t>(tok) * g.ldo + head * 64 + 2 * lane) =
+                temporal_last_core<TC>(qkv[0], qkv[1], qkv[2], cache, static_cast<size_t>(P) * 2 * D, D, cs);
+        }
+    }
+}
+
+template <int EPI, int FUSE>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const SkinnyParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -171,11 +273,13 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 128) SK_STAMP(0);                                       // kernel entry
+    // fused modes launch extra CTAs that own token rows in the reduce but no tile of the GEMM
+    const bool gemm_cta = FUSE == SK_FUSE_NONE || static_cast<int>(blockIdx.x) < p.gemm_ctas;
     const int rb = blockIdx.x / S, split = blockIdx.x - rb * S;
     const int kc0 = split * chunks;
     const uint32_t tmem_cols = tiles * SK_NT <= 256 ? 256u : 512u;
 
-    if (warp == 0 && lane == 0) {
+    if (gemm_cta && warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmW);
         tma_prefetch_desc(&tmA);
         mbar_init(bar_w, 1);
@@ -183,18 +287,21 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         mbar_init(bar_acc, 1);
         fence_barrier_init();
     }
-    if (warp == 2) {
+    if (gemm_cta && warp == 2) {
         tmem_alloc(tmem_slot, tmem_cols);
         tmem_relinquish();
     }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = gemm_cta ? *tmem_slot : 0u;
     pdl_trigger();
     if (threadIdx.x == 128) SK_STAMP(1);                                       // set-up done
 
-    if (warp == 0) {
+    if (!gemm_cta) {
+        if (warp >= 4) l2_prefetch_share(p.g.prefetch, p.g.prefetch_bytes, (blockIdx.x * 4 + (warp - 4)) * 32 + lane, gridDim.x * 128);
+        pdl_wait();
+    } else if (warp == 0) {
         if (lane == 0) {
             mbar_arrive_expect_tx(bar_w, chunks * SK_W_CHUNK);
             tma_load_3d(sW, &tmW, bar_w, 0, rb * 128, kc0);
@@ -254,7 +361,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             }
         }
     }
-    if (S > 1) {
+    if (S > 1 && gemm_cta) {
         // ---- accumulator -> fp32 partial tile ws[cta][token][128 weight rows], drained by ALL 8 warps: warp w reads the
         // TMEM lane quadrant w % 4, warps 4-7 the first half of the token columns, warps 0-3 (whose producer / MMA roles
         // are over) the second half
@@ -285,17 +392,19 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             int* arrive = p.counters + 2 * rb;
             SK_STAMP(5);                                                       // partials written + fenced
             atomicAdd(arrive, 1);
-            uint32_t spins = 0;
-            while (ld_acquire_gpu(arrive) < S) {
-                __nanosleep(64);
-                if (++spins > (1u << 24)) {
-                    printf("gtav: split-K rendezvous timed out (block %d)\n", blockIdx.x);
-                    __trap();
+            if (FUSE == SK_FUSE_NONE) {
+                uint32_t spins = 0;
+                while (ld_acquire_gpu(arrive) < S) {
+                    __nanosleep(64);
+                    if (++spins > (1u << 24)) {
+                        printf("gtav: split-K rendezvous timed out (block %d)\n", blockIdx.x);
+                        __trap();
+                    }
                 }
             }
         }
     }
-    if (S > 1) {
+    if (S > 1 && FUSE == SK_FUSE_NONE) {
         // all 8 warps reduce once the rendezvous of the row block has completed
         __syncthreads();
         if (threadIdx.x == 128) SK_STAMP(6);                                   // rendezvous passed
@@ -322,9 +431,58 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             }
         }
     }
+    if (FUSE != SK_FUSE_NONE) {
+        // ---- every CTA waits for ALL row blocks (thread i polls block i's counter), then owns whole token rows
+        const int rbs = p.g.N / 128, total = tiles * SK_NT;
+        if (static_cast<int>(threadIdx.x) < rbs) {
+            const int* arrive = p.counters + 2 * threadIdx.x;
+            uint32_t spins = 0;
+            while (ld_acquire_gpu(arrive) < S) {
+                __nanosleep(64);
+                if (++spins > (1u << 24)) {
+                    printf("gtav: split-K rendezvous timed out (block %d, row block %d)\n", blockIdx.x, threadIdx.x);
+                    __trap();
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 128) SK_STAMP(6);
+        if (FUSE == SK_FUSE_LN) {
+            switch (S) {
+                case 2: skinny_reduce_ln<2>(p, total, warp, lane, sW); break;
+                case 4: skinny_reduce_ln<4>(p, total, warp, lane, sW); break;
+                case 8: skinny_reduce_ln<8>(p, total, warp, lane, sW); break;
+                case 16: skinny_reduce_ln<16>(p, total, warp, lane, sW); break;
+                default: __trap();
+            }
+        } else {
+            switch (p.f.ctx_frames) {                                          // S == 4 (checked on the host)
+                case 0: skinny_reduce_tattn<4, 0>(p, total, warp, lane); break;
+                case 1: skinny_reduce_tattn<4, 1>(p, total, warp, lane); break;
+                case 2: skinny_reduce_tattn<4, 2>(p, total, warp, lane); break;
+                case 3: skinny_reduce_tattn<4, 3>(p, total, warp, lane); break;
+                case 4: skinny_reduce_tattn<4, 4>(p, total, warp, lane); break;
+                case 5: skinny_reduce_tattn<4, 5>(p, total, warp, lane); break;
+                case 6: skinny_reduce_tattn<4, 6>(p, total, warp, lane); break;
+                case 7: skinny_reduce_tattn<4, 7>(p, total, warp, lane); break;
+                default: __trap();
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 128) {
+            SK_STAMP(7);
+            // the last CTA past the rendezvous clears every counter for the next launch (slot 1 = departures)
+            const int old = atomicAdd(p.counters + 1, 1);
+            if (old == static_cast<int>(gridDim.x) - 1) {
+                p.counters[1] = 0;
+                __threadfence();
+                for (int r = 0; r < rbs; ++r) atomicExch(p.counters + 2 * r, 0);
+            }
+        }
+    }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+    if (gemm_cta && warp == 2) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -360,7 +518,7 @@ int skinny_pick_splits(int M, int N, int K) {
 size_t skinny_workspace_bytes(int M) { return static_cast<size_t>(160) * M * 128 * sizeof(float); }
 
 int skinny_prepare(SkinnyOp* op, const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi, float* ws,
-                   int* counters, int splits_override) {
+                   int* counters, int splits_override, const SkinnyFuseParams* fuse) {
     if (!skinny_supported(p.M, p.N, p.K, epi)) {
         set_error("skinny gemm: unsupported shape/epilogue M=%d N=%d K=%d epi=%d", p.M, p.N, p.K, epi);
         return -1;
@@ -384,36 +542,58 @@ int skinny_prepare(SkinnyOp* op, const bf16* A, int lda, const bf16* W, int ldw,
     op->ws = ws;
     op->counters = counters;
     op->trace = nullptr;
+    op->f = SkinnyFuseParams{};
+    op->grid = rbs * S;
+    if (fuse != nullptr && fuse->mode != SK_FUSE_NONE) {
+        // per-token reduce: one CTA per token row up to the SM count (all CTAs must be co-resident: they rendezvous)
+        const bool ln_ok = fuse->mode == SK_FUSE_LN && epi == EPI_BIAS_GATE_RES && p.N == 1024 && S > 1 && fuse->ln_out != nullptr &&
+                           fuse->ln_mod != nullptr && fuse->ln_mod_ld % 8 == 0 && fuse->ln_shift_off % 8 == 0 && fuse->ln_scale_off % 8 == 0;
+        const bool ta_ok = fuse->mode == SK_FUSE_TATTN && epi == EPI_STORE && p.N == 3072 && S == 4 && fuse->rot != nullptr &&
+                           fuse->ctx_frames >= 0 && fuse->ctx_frames <= 7 && (fuse->ctx_frames == 0 || fuse->kv_cache != nullptr) &&
+                           fuse->positions > 0 && p.M % fuse->positions == 0;
+        if (!ln_ok && !ta_ok) {
+            set_error("skinny gemm: fused reduce mode %d does not fit M=%d N=%d K=%d epi=%d splits=%d", fuse->mode, p.M, p.N, p.K, epi, S);
+            return -1;
+        }
+        op->f = *fuse;
+        int sms = 148, dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) sms = n;
+        const int want = p.M < sms ? p.M : sms;
+        if (want > op->grid) op->grid = want;
+    }
     int rc = make_tmap_3d(&op->tmW, W, p.N, p.K, ldw, 128, op->chunks);
     if (rc) return rc;
     return make_tmap_3d(&op->tmA, A, p.M, p.K, lda, SK_NT, op->chunks);
 }
 
-template <int EPI>
+template <int EPI, int FUSE>
 static int skinny_launch(const SkinnyOp* op, cudaStream_t stream) {
     static bool configured = false;
-    auto kern = gemm_skinny_kernel<EPI>;
+    auto kern = gemm_skinny_kernel<EPI, FUSE>;
     if (!configured) {
         GTAV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BUDGET + 2048));
         configured = true;
     }
     SkinnyParams sp;
-    sp.g = op->p; sp.splits = op->splits; sp.chunks = op->chunks; sp.tiles = op->tiles; sp.ws = op->ws; sp.counters = op->counters;
+    sp.g = op->p; sp.f = op->f; sp.splits = op->splits; sp.chunks = op->chunks; sp.tiles = op->tiles; sp.ws = op->ws;
+    sp.counters = op->counters; sp.gemm_ctas = (op->p.N / 128) * op->splits;
     sp.trace = op->trace;
     // At least half of the SM's shared memory, so that exactly one CTA of this kernel fits on an SM: the CTAs of a
     // row block wait for each other, and a second CTA on the same SM could block in tcgen05.alloc behind a waiting one.
     size_t smem = static_cast<size_t>(op->chunks) * (SK_W_CHUNK + op->tiles * SK_A_CHUNK) + 64 + 1024;
     if (smem < 120 * 1024) smem = 120 * 1024;
-    GTAV_CUDA_OK(launch_k(kern, dim3((op->p.N / 128) * op->splits), dim3(SK_THREADS), smem, stream, op->tmW, op->tmA, sp));
+    GTAV_CUDA_OK(launch_k(kern, dim3(op->grid), dim3(SK_THREADS), smem, stream, op->tmW, op->tmA, sp));
     return 0;
 }
 
 int skinny_run(const SkinnyOp* op, cudaStream_t stream) {
+    if (op->f.mode == SK_FUSE_LN) return skinny_launch<EPI_BIAS_GATE_RES, SK_FUSE_LN>(op, stream);
+    if (op->f.mode == SK_FUSE_TATTN) return skinny_launch<EPI_STORE, SK_FUSE_TATTN>(op, stream);
     switch (op->epi) {
-        case EPI_STORE: return skinny_launch<EPI_STORE>(op, stream);
-        case EPI_BIAS: return skinny_launch<EPI_BIAS>(op, stream);
-        case EPI_BIAS_GELU_TANH: return skinny_launch<EPI_BIAS_GELU_TANH>(op, stream);
-        case EPI_BIAS_GATE_RES: return skinny_launch<EPI_BIAS_GATE_RES>(op, stream);
+        case EPI_STORE: return skinny_launch<EPI_STORE, SK_FUSE_NONE>(op, stream);
+        case EPI_BIAS: return skinny_launch<EPI_BIAS, SK_FUSE_NONE>(op, stream);
+        case EPI_BIAS_GELU_TANH: return skinny_launch<EPI_BIAS_GELU_TANH, SK_FUSE_NONE>(op, stream);
+        case EPI_BIAS_GATE_RES: return skinny_launch<EPI_BIAS_GATE_RES, SK_FUSE_NONE>(op, stream);
     }
     set_error("skinny gemm: unknown epilogue %d", op->epi);
     return -1;

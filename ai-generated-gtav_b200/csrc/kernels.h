@@ -90,9 +90,27 @@ int make_tmap_3d(CUtensorMap* out, const bf16* ptr, uint64_t rows, uint64_t cols
 // ---------------------------------------------------------------- weight-streaming GEMM (gemm_skinny.cu)
 // Same contract as the GEMM above for M = 144 * {1,2,3} token rows (last-frame DiT step): operands swapped
 // (weights on the UMMA M side), K split over CTAs with an in-kernel deterministic reduction.
+// Row-wise work fused into the split-K reduce (every CTA then owns whole token rows, see gemm_skinny.cu):
+//   SK_FUSE_LN    (N = 1024, EPI_BIAS_GATE_RES): besides out (the new residual stream), ln_out [M, 1024] receives
+//                 LN(out row) * (1 + scale) + shift with shift / scale at ln_mod + frame * ln_mod_ld + {ln_shift_off, ln_scale_off}
+//                 (frame from the GEMM's frame_row / rows_per_frame) - the launch_ln_modulate that would follow;
+//   SK_FUSE_TATTN (N = 3072, EPI_STORE, 4 splits): out [M, 1024] receives the last-frame temporal attention of the q|k|v
+//                 row against kv_cache (launch_attention_temporal_last's arguments) instead of the row itself.
+enum SkinnyFuse : int { SK_FUSE_NONE = 0, SK_FUSE_LN = 1, SK_FUSE_TATTN = 2 };
+struct SkinnyFuseParams {
+    int mode;
+    bf16* ln_out;
+    const bf16* ln_mod;
+    int ln_mod_ld, ln_shift_off, ln_scale_off;
+    const bf16* kv_cache;
+    const float2* rot;
+    int ctx_frames, positions;
+};
 struct SkinnyOp {
     CUtensorMap tmW, tmA;
     GemmParams p;
+    SkinnyFuseParams f;
+    int grid;         // CTAs launched: (N/128) * splits, or more in the fused modes (reduce-only CTAs)
     int epi, splits, chunks, tiles;
     float* ws;        // fp32 partial-sum workspace, skinny_workspace_bytes(M)
     int* counters;    // 128 zero-initialised ints (rendezvous counters, self-resetting)
@@ -102,7 +120,7 @@ bool skinny_supported(int M, int N, int K, int epi);
 int skinny_pick_splits(int M, int N, int K);
 size_t skinny_workspace_bytes(int M);
 int skinny_prepare(SkinnyOp* op, const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi, float* ws,
-                   int* counters, int splits_override = 0);
+                   int* counters, int splits_override = 0, const SkinnyFuseParams* fuse = nullptr);
 int skinny_run(const SkinnyOp* op, cudaStream_t stream);
 
 // ---------------------------------------------------------------- persistent last-frame step (dit_step_mega.cu)

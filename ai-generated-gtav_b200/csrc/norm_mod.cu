@@ -6,6 +6,7 @@
 // registers), output rounded once to bf16 - the rounding the following Linear's autocast applies.
 #include "common.cuh"
 #include "kernels.h"
+#include "ln_row.cuh"
 
 namespace gtav {
 
@@ -40,58 +41,28 @@ ln_rows_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int M, const 
         }
     }
     float v[CHUNKS][8];
-    float sum = 0.f;
-#pragma unroll
-    for (int c = 0; c < CHUNKS; ++c) {
-        const uint32_t uw[4] = {xu[c].x, xu[c].y, xu[c].z, xu[c].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float2 f = unpack_bf16x2(uw[j]);
-            v[c][2 * j] = f.x;
-            v[c][2 * j + 1] = f.y;
-            sum += f.x + f.y;
-        }
-    }
-    const float mean = warp_sum(sum) * (1.0f / D);
-    float sq = 0.f;
-#pragma unroll
-    for (int c = 0; c < CHUNKS; ++c)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float d = v[c][j] - mean;
-            sq += d * d;
-        }
-    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + 1e-6f);
+    float mean, rstd;
+    ln_row_stats<CHUNKS>(xu, v, mean, rstd);
 
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
         const int col = c * 256 + lane * 8;
-        float y[8];
+        uint4 o;
         if (AFFINE) {
+            float y[8];
             const float4 w0 = *reinterpret_cast<const float4*>(w + col), w1 = *reinterpret_cast<const float4*>(w + col + 4);
             const float4 b0 = *reinterpret_cast<const float4*>(b + col), b1 = *reinterpret_cast<const float4*>(b + col + 4);
             const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) y[j] = (v[c][j] - mean) * rstd * ww[j] + bb[j];
+            o.x = pack_bf16x2(y[0], y[1]);
+            o.y = pack_bf16x2(y[2], y[3]);
+            o.z = pack_bf16x2(y[4], y[5]);
+            o.w = pack_bf16x2(y[6], y[7]);
         } else {
-            const uint4 sh = shu[c], sc = scu[c];
-            const uint32_t shw[4] = {sh.x, sh.y, sh.z, sh.w}, scw[4] = {sc.x, sc.y, sc.z, sc.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 s2 = unpack_bf16x2(shw[j]), c2 = unpack_bf16x2(scw[j]);
-                // scale + 1e-6 and 1 + scale are bf16 tensor ops in the reference (model/dit.py:26-27)
-                const float m0 = bf16_round(1.0f + bf16_round(c2.x + 1e-6f));
-                const float m1 = bf16_round(1.0f + bf16_round(c2.y + 1e-6f));
-                y[2 * j] = (v[c][2 * j] - mean) * rstd * m0 + s2.x;
-                y[2 * j + 1] = (v[c][2 * j + 1] - mean) * rstd * m1 + s2.y;
-            }
+            o = ln_modulate_slice(v[c], mean, rstd, shu[c], scu[c]);
         }
-        uint4 o;
-        o.x = pack_bf16x2(y[0], y[1]);
-        o.y = pack_bf16x2(y[2], y[3]);
-        o.z = pack_bf16x2(y[4], y[5]);
-        o.w = pack_bf16x2(y[6], y[7]);
         *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * D + col) = o;
     }
 }

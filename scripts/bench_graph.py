@@ -123,7 +123,8 @@ def engine_steps():
     t = torch.tensor([[15, 15, 15, 15, 500]], device=dev)
     rows = torch.arange(5, dtype=torch.int32, device=dev)
     out = torch.empty((1, 1, 16, 18, 32), dtype=torch.bfloat16, device=dev)
-    for label, env in (("default (weight-streaming GEMM, L2 prefetch)", {}), ("no prefetch", {"GTAV_PREFETCH": "0"}),
+    for label, env in (("default (weight-streaming GEMM, L2 prefetch, LN + temporal attention in the reduce)", {}),
+                       ("separate LN / temporal-attention kernels", {"GTAV_FUSE": "0"}), ("no prefetch", {"GTAV_PREFETCH": "0"}),
                        ("tiled GEMM everywhere", {"GTAV_SKINNY": "0"}),
                        ("no PDL", {"GTAV_PDL_OFF_NOTE": "set GTAV_PDL=0 before start to test"})):
         if "GTAV_PDL_OFF_NOTE" in env:

@@ -16,6 +16,7 @@ bench_dense) TAILN=5 run bench_dense python bench.py --algorithm dense --steps 1
 bench_c3) TAILN=5 run bench_c3 python bench.py --workload c3 --steps 1 --warmup 3 --no-cpu-baseline ;;
 bench_c1) TAILN=5 run bench_c1 python bench.py --workload c1 --steps 2 --warmup 3 --no-cpu-baseline ;;
 kbench) TAILN=40 run b_kernels python scripts/bench_kernels.py ;;
+engine) TAILN=12 run b_engine python scripts/bench_graph.py --engine ;;
 klight) TAILN=60 run b_light python scripts/bench_kernels.py --light ;;
 ncu) TAILN=3 run ncu_list ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 1200 --csv --log-file gpurun_out/launches.csv python bench.py --workload c1 --steps 1 --warmup 1 --no-cpu-baseline --no-dense ;;
 ncu_full) TAILN=3 run ncu_full ncu --set full --clock-control none --import-source on -k regex:${NCU_K:-gemm_skinny} -s ${NCU_S:-200} -c 4 -o gpurun_out/prof_${NCU_NAME:-skinny} python bench.py --workload c1 --steps 1 --warmup 1 --no-cpu-baseline --no-dense ;;

@@ -110,6 +110,31 @@ def test_dit_last_frame_split_equals_dense(monkeypatch, mode):
         assert torch.equal(split, again), "last-frame pass is not deterministic"
 
 
+def test_fused_reduce_equals_separate_kernels(monkeypatch):
+    """LayerNorm + modulate and the last-frame temporal attention folded into the weight-streaming GEMMs' reduce
+    (GTAV_FUSE, default on) give the same bits as the stand-alone kernels (GTAV_FUSE=0): same row code, same order."""
+    from gtav_b200.model.dit import DiT
+    sd = make_dit_state(DiTConfig(depth=3), seed=0)
+    outs = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("GTAV_FUSE", fuse)
+        monkeypatch.setenv("GTAV_SKINNY", "1")
+        monkeypatch.setenv("GTAV_MEGA", "0")
+        model = DiT(depth=3)
+        model.load_state_dict(sd, strict=True)
+        model = model.cuda().eval()
+        res = []
+        for B, T, seed, actions in ((1, 5, 91, True), (1, 3, 92, False), (1, 1, 93, False), (2, 4, 94, True), (1, 5, 95, True)):
+            x = seeded_randn((B, T, 16, 18, 32), seed).cuda()
+            t = torch.randint(0, 1000, (B, T), generator=torch.Generator().manual_seed(seed)).cuda()
+            a = w_key_actions(B, T).cuda() if actions else None
+            res.append(model.forward_last_frame(x, t, a).clone())
+        outs[fuse] = res
+    for i, (a, b) in enumerate(zip(outs["1"], outs["0"])):
+        assert torch.isfinite(a.float()).all()
+        assert torch.equal(a, b), f"case {i}: fused reduce differs from separate kernels, max-abs {float((a.float() - b.float()).abs().max())}"
+
+
 @pytest.mark.parametrize("mega", ["1", "0"])
 def test_step_kernel_full_depth_vs_reference_golden(golden, monkeypatch, mega):
     """The persistent step kernel on the real 16-block DiT (B = 1, T = 5): last frame of the v-prediction against the
