@@ -103,8 +103,9 @@ attn_temporal_last_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, 
     const float2 qx = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(base));
     const float2 kx = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(base + D));
     const float2 vx = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(base + 2 * D));
-    *reinterpret_cast<uint32_t*>(out + qrow * D + head * 64 + 2 * lane) =
-        temporal_last_core<TC>(qx, kx, vx, cache, static_cast<size_t>(P) * 2 * D, D, rot[TC * 32 + lane]);
+    uint32_t kc[TC > 0 ? TC : 1], vc[TC > 0 ? TC : 1];
+    temporal_cache_load(kc, vc, TC, cache, static_cast<size_t>(P) * 2 * D, D);
+    *reinterpret_cast<uint32_t*>(out + qrow * D + head * 64 + 2 * lane) = temporal_last_core<TC>(qx, kx, vx, kc, vc, rot[TC * 32 + lane]);
 }
 
 int launch_attention_temporal_last(const bf16* qkv, bf16* out, int B, int ctx_frames, int positions, int heads,

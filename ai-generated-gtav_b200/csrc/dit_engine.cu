@@ -90,7 +90,7 @@ void carve(gtav_dit_plan_s* p, void* ws, size_t* total) {
     const int m_last = p->B * e->tokens;
     size_t ws_bytes = p->B <= 3 ? skinny_workspace_bytes(m_last) : 0;
     p->sk_ws = reinterpret_cast<float*>(c.take(ws_bytes / sizeof(bf16)));
-    p->sk_counters = reinterpret_cast<int*>(c.take(1024));      // 512 ints: 2 per row / column block
+    p->sk_counters = reinterpret_cast<int*>(c.take(1024));      // 512 ints: 4 per rendezvous group (gemm_skinny.cu)
     if (p->B == 1) {
         p->mega_halves = reinterpret_cast<MegaHalfDev*>(c.take(static_cast<size_t>(2 * e->cfg.depth) * sizeof(MegaHalfDev) / sizeof(bf16)));
         p->mega_sync = reinterpret_cast<unsigned*>(c.take(mega_sync_bytes() / sizeof(bf16)));
@@ -269,10 +269,21 @@ int run_backbone(gtav_dit_plan_s* p, const Shape* sh, int mode, const void* x, i
         if ((rc = mega_run(mp, stream))) return rc;
     }
     bool hn_ready = false;                  // the previous fc2's reduce already wrote this half's LN1 output
+    // GTAV_ENGINE_TRACE=<device address>: phase time stamps of every weight-streaming GEMM of this pass, [launch][160][8]
+    // int64 globaltimer ns (scripts/trace_step.py); profiling aid, unset in production
+    long long* trace_base = nullptr;
+    if (const char* tr = getenv("GTAV_ENGINE_TRACE")) trace_base = reinterpret_cast<long long*>(strtoull(tr, nullptr, 0));
+    int trace_k = 0;
+    auto run_skinny = [&](const SkinnyOp& op0) {
+        SkinnyOp o = op0;
+        o.p.frame_row = frame_row;
+        if (trace_base != nullptr) o.trace = trace_base + static_cast<size_t>(trace_k++) * 160 * 8;
+        return skinny_run(&o, stream);
+    };
     for (int i = 0; i < 2 * c.depth && !mega; ++i) {
         const int off = i * 6 * D;          // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
         if (!hn_ready && (rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, off, off + D, frame_row, S, stream))) return rc;
-        if (sh->sk[0]) rc = skinny_run(&sh->s_qkv[i], stream);
+        if (sh->sk[0]) rc = run_skinny(sh->s_qkv[i]);
         else rc = gemm_run(&sh->g_qkv[i], stream);
         if (rc) return rc;
         if (sh->s_qkv.size() && sh->sk[0] && sh->s_qkv[i].f.mode == SK_FUSE_TATTN) {
@@ -286,9 +297,7 @@ int run_backbone(gtav_dit_plan_s* p, const Shape* sh, int mode, const void* x, i
         }
         if (rc) return rc;
         if (sh->sk[1]) {
-            SkinnyOp o = sh->s_out[i];
-            o.p.frame_row = frame_row;
-            rc = skinny_run(&o, stream);
+            rc = run_skinny(sh->s_out[i]);
         } else {
             GemmOp o = sh->g_out[i];
             o.p.frame_row = frame_row;
@@ -296,13 +305,11 @@ int run_backbone(gtav_dit_plan_s* p, const Shape* sh, int mode, const void* x, i
         }
         if (rc) return rc;
         if (!sh->fuse_ln && (rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, off + 3 * D, off + 4 * D, frame_row, S, stream))) return rc;
-        if (sh->sk[2]) rc = skinny_run(&sh->s_fc1[i], stream);
+        if (sh->sk[2]) rc = run_skinny(sh->s_fc1[i]);
         else rc = gemm_run(&sh->g_fc1[i], stream);
         if (rc) return rc;
         if (sh->sk[3]) {
-            SkinnyOp o = sh->s_fc2[i];
-            o.p.frame_row = frame_row;
-            rc = skinny_run(&o, stream);
+            rc = run_skinny(sh->s_fc2[i]);
         } else {
             GemmOp o = sh->g_fc2[i];
             o.p.frame_row = frame_row;

@@ -4,19 +4,20 @@
 // Same reference ops as gemm_sm100.cu (to_qkv / to_out / Mlp.fc1 / Mlp.fc2 of reference
 // model/attention.py:27-28,86-87 and model/dit.py:171-198) - this is the shape they take once the
 // context frames' K/V are cached and only the frame being denoised is recomputed (M = 144*B).
-// At that size the op is bound by streaming W from HBM and A from L2, not by the tensor pipe, so the
-// kernel is organised around getting all SMs to pull bytes at once:
+// At that size the op is bound by moving bytes (W from HBM, A and the split-K partials through L2) and by the
+// latency chain of its phases, not by the tensor pipe, so the kernel is organised around getting all SMs to pull
+// bytes at once and around overlapping consecutive launches:
 //   * operands are swapped: the UMMA "M" side is a block of 128 weight rows, the "N" side one
 //     144-token frame tile (a legal UMMA N, no padding), accumulator D[128 x 144] fp32 in TMEM;
-//   * K is split over S CTAs per weight-row block so that (N/128)*S ~ the SM count; every CTA
-//     loads its whole operand slab with ONE TMA instruction per operand (3-D box spanning all its
-//     64-wide K chunks: measured on B200, a TMA instruction costs ~0.4 us of issue time per warp
-//     whatever its size, so few large boxes from two producer warps beat many 16 KB ones);
-//   * the W slab is requested before griddepcontrol.wait (weights do not depend on the previous
-//     kernel), so HBM latency hides behind the previous kernel's tail;
+//   * K is split over S CTAs per weight-row block so that (N/128)*S ~ the SM count; the W slab is ONE TMA box
+//     (3-D box spanning all its 64-wide K chunks: several small boxes per operand measured slower, bench_graph.py);
+//   * the W slab is requested before griddepcontrol.wait (weights do not depend on the previous kernel);
 //   * partial accumulators go to an fp32 workspace (L2), the S CTAs of a row block meet on a
 //     counter, and each reduces + runs the fused epilogue for its 1/S share of the tokens, summing
-//     the partials in split order (deterministic).
+//     the partials in split order (deterministic);
+//   * optionally the reduce is done per token row by every CTA (plus reduce-only CTAs up to one per token), which lets
+//     the row-wise kernel that would follow - LayerNorm + modulate, or the last-frame temporal attention - run inside
+//     it; everything those need besides the partial sums is loaded BEFORE the rendezvous.
 // Warp roles (256 threads): 0 = W producer, 1 = A producer, 2 = TMEM allocator + MMA issuer, 4-7 = L2 prefetch of
 // the next GEMM's weights; all 8 warps drain the accumulator (one TMEM lane quadrant each, half of the columns) and reduce.
 #include "attn_temporal_core.cuh"
@@ -30,7 +31,9 @@ static constexpr int SK_THREADS = 256;
 static constexpr int SK_NT = 144;                  // tokens per tile (one frame)
 static constexpr int SK_W_CHUNK = 128 * 128;       // bytes: 128 weight rows x 64 bf16
 static constexpr int SK_A_CHUNK = SK_NT * 128;     // bytes: 144 tokens x 64 bf16
-static constexpr int SK_SMEM_BUDGET = 200 * 1024;
+static constexpr int SK_SMEM_BUDGET = 200 * 1024;  // operand bytes per CTA
+static constexpr int SK_TAIL_BYTES = 128 + 4096 + 2048;   // barriers | shift + scale of the fused LayerNorm | one bf16 row
+static constexpr int SK_TMAX = 7;                  // cached context frames of the fused temporal attention
 
 struct SkinnyParams {
     GemmParams g;
@@ -57,6 +60,31 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Rendezvous of the n CTAs of a group (one thread per CTA) on grp[0..3] = {count A, count B, which, -}, all zero before
+// the first launch.  `which` (read by the caller BEFORE this CTA's arrival, any time after griddepcontrol.wait - the flip
+// needs every CTA's arrival, so the value read cannot be the flipped one) selects the counter this launch counts on; the
+// other one still holds the previous launch's total and is cleared here, and `which` is flipped for the next launch, by
+// every CTA that gets through (same values from everyone: plain stores, nobody waits for them).  So an arrival is one
+// fire-and-forget reduction plus polling, and the kernel's exit path carries no atomic round trip (the former
+// departure counter cost ~0.7 us per launch; a returning atomicAdd on arrival costs the same: scripts/trace_step.py).
+// The caller has made its partial sums visible (fence + CTA barrier) before arriving.
+__device__ __forceinline__ void skinny_rendezvous(int* grp, int n, int which) {
+    int* cnt = grp + (which & 1);
+    asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(cnt) : "memory");
+    uint32_t spins = 0;
+    while (ld_acquire_gpu(cnt) < n) {
+        __nanosleep(32);
+        if (++spins > (1u << 24)) {
+            printf("gtav: split-K rendezvous timed out (block %d)\n", blockIdx.x);
+            __trap();
+        }
+    }
+    *reinterpret_cast<volatile int*>(grp + ((which & 1) ^ 1)) = 0;
+    *reinterpret_cast<volatile int*>(grp + 2) = (which & 1) ^ 1;
+}
 __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -82,14 +110,29 @@ __device__ __forceinline__ void skinny_store(const GemmParams& g, int tok, int n
     g.out[static_cast<size_t>(tok) * g.ldo + n] = __float2bfloat16_rn(y);
 }
 
-// Four consecutive output columns n..n+3 of token `tok` (split-K reduce path: 8-byte vector accesses): the epilogue's
-// bf16 results, packed.
+// The epilogue's vector operands for four consecutive output columns n..n+3 of one token (packed bf16).
+struct Epi4Ops {
+    uint2 bias, gate, res;
+};
 template <int EPI>
-__device__ __forceinline__ uint2 skinny_epi4(const GemmParams& g, int tok, int n, float4 acc) {
+__device__ __forceinline__ Epi4Ops skinny_epi4_load(const GemmParams& g, int tok, int n) {
+    Epi4Ops o;
+    o.bias = o.gate = o.res = make_uint2(0u, 0u);
+    if (EPI != EPI_STORE) o.bias = *reinterpret_cast<const uint2*>(g.bias + n);
+    if (EPI == EPI_BIAS_GATE_RES) {
+        int f = tok / g.rows_per_frame;
+        if (g.frame_row != nullptr) f = g.frame_row[f];
+        o.gate = *reinterpret_cast<const uint2*>(g.gate + static_cast<size_t>(f) * g.gate_ld + n);
+        o.res = *reinterpret_cast<const uint2*>(g.res + static_cast<size_t>(tok) * g.ldr + n);
+    }
+    return o;
+}
+// Four consecutive output columns of one token (split-K reduce path): the epilogue's bf16 results, packed.
+template <int EPI>
+__device__ __forceinline__ uint2 skinny_epi4(float4 acc, const Epi4Ops& e) {
     float y[4] = {acc.x, acc.y, acc.z, acc.w};
     if (EPI != EPI_STORE) {
-        const uint2 bv = *reinterpret_cast<const uint2*>(g.bias + n);
-        const float2 b0 = unpack_bf16x2(bv.x), b1 = unpack_bf16x2(bv.y);
+        const float2 b0 = unpack_bf16x2(e.bias.x), b1 = unpack_bf16x2(e.bias.y);
         y[0] += b0.x; y[1] += b0.y; y[2] += b1.x; y[3] += b1.y;
     }
 #pragma unroll
@@ -98,11 +141,7 @@ __device__ __forceinline__ uint2 skinny_epi4(const GemmParams& g, int tok, int n
 #pragma unroll
         for (int j = 0; j < 4; ++j) y[j] = gelu_tanh_f(y[j]);
     } else if (EPI == EPI_BIAS_GATE_RES) {
-        int f = tok / g.rows_per_frame;
-        if (g.frame_row != nullptr) f = g.frame_row[f];
-        const uint2 gv = *reinterpret_cast<const uint2*>(g.gate + static_cast<size_t>(f) * g.gate_ld + n);
-        const uint2 rv = *reinterpret_cast<const uint2*>(g.res + static_cast<size_t>(tok) * g.ldr + n);
-        const float2 g0 = unpack_bf16x2(gv.x), g1 = unpack_bf16x2(gv.y), r0 = unpack_bf16x2(rv.x), r1 = unpack_bf16x2(rv.y);
+        const float2 g0 = unpack_bf16x2(e.gate.x), g1 = unpack_bf16x2(e.gate.y), r0 = unpack_bf16x2(e.res.x), r1 = unpack_bf16x2(e.res.y);
         y[0] = r0.x + bf16_round(g0.x * y[0]);
         y[1] = r0.y + bf16_round(g0.y * y[1]);
         y[2] = r1.x + bf16_round(g1.x * y[2]);
@@ -114,16 +153,20 @@ __device__ __forceinline__ uint2 skinny_epi4(const GemmParams& g, int tok, int n
     return o;
 }
 template <int EPI>
-__device__ __forceinline__ void skinny_store4(const GemmParams& g, int tok, int n, float4 acc) {
-    *reinterpret_cast<uint2*>(g.out + static_cast<size_t>(tok) * g.ldo + n) = skinny_epi4<EPI>(g, tok, n, acc);
+__device__ __forceinline__ void skinny_store4(const GemmParams& g, int tok, int n, float4 acc, uint2 bias) {
+    Epi4Ops e;
+    if (EPI == EPI_BIAS_GATE_RES) e = skinny_epi4_load<EPI>(g, tok, n);
+    e.bias = bias;
+    *reinterpret_cast<uint2*>(g.out + static_cast<size_t>(tok) * g.ldo + n) = skinny_epi4<EPI>(acc, e);
 }
 
 // Sum the S partial tiles of this row block for tokens lo + wid, lo + wid + 8, ... (one warp per token, lane = 4
 // consecutive weight rows) in split order and run the epilogue.  S is a template parameter so that all S loads of a
-// token are in flight together: the loop is otherwise a chain of exposed L2 latencies.
+// token are in flight together: the loop is otherwise a chain of exposed L2 latencies.  bias: this lane's four
+// columns, loaded by the caller before the rendezvous.
 template <int EPI, int S>
 __device__ __forceinline__ void skinny_reduce(const GemmParams& g, const float* part, int total, int lo, int hi, int wid, int lane,
-                                              int n0) {
+                                              int n0, uint2 bias) {
     const float* base = part + 4 * lane;
     if (S <= 4) {
         // few splits: a warp's tokens (at most 5 per 144-token tile share) are loaded together, so the whole reduce costs
@@ -146,7 +189,7 @@ __device__ __forceinline__ void skinny_reduce(const GemmParams& g, const float* 
                     float4 acc = v[it][0];
 #pragma unroll
                     for (int s2 = 1; s2 < S; ++s2) { acc.x += v[it][s2].x; acc.y += v[it][s2].y; acc.z += v[it][s2].z; acc.w += v[it][s2].w; }
-                    skinny_store4<EPI>(g, tok, n0 + 4 * lane, acc);
+                    skinny_store4<EPI>(g, tok, n0 + 4 * lane, acc, bias);
                 }
             }
         }
@@ -161,19 +204,39 @@ __device__ __forceinline__ void skinny_reduce(const GemmParams& g, const float* 
         float4 acc = v[0];
 #pragma unroll
         for (int s2 = 1; s2 < S; ++s2) { acc.x += v[s2].x; acc.y += v[s2].y; acc.z += v[s2].z; acc.w += v[s2].w; }
-        skinny_store4<EPI>(g, tok, n0 + 4 * lane, acc);
+        skinny_store4<EPI>(g, tok, n0 + 4 * lane, acc, bias);
     }
 }
 
 // ---- fused reduces: the CTAs meet on ALL row-block counters and every CTA then owns whole token rows (token
 // blockIdx.x, blockIdx.x + gridDim.x, ...), so that row-wise work that follows the Linear can run right here instead
-// of in another kernel of the latency-bound last-frame chain.
+// of in another kernel of the latency-bound last-frame chain.  Their operands other than the partial sums (epilogue
+// vectors, modulation vectors, K/V cache) are loaded by the *_preload functions, which the kernel calls right after
+// griddepcontrol.wait: by the time the rendezvous completes they are in registers / shared memory.
 //
 // SK_FUSE_LN (N = 1024, gated-residual epilogue: to_out and fc2 of reference model/dit.py:205-224): warp w sums the
 // partials of row block w, the new residual-stream row goes to g.out and, as bf16, to shared memory; warp 0 then
 // runs the NEXT LayerNorm + modulate on it with ln_rows_kernel's own code (same bits as the stand-alone kernel).
+// smod: 2 KB shift | 2 KB scale of the token's frame, filled cooperatively (thread i: 16 bytes).
+__device__ __forceinline__ Epi4Ops skinny_ln_preload(const SkinnyParams& p, int tok, int warp, uint8_t* smod) {
+    const GemmParams& g = p.g;
+    const SkinnyFuseParams& f = p.f;
+    int fr = tok / g.rows_per_frame;
+    if (g.frame_row != nullptr) fr = g.frame_row[fr];
+    const bf16* mrow = f.ln_mod + static_cast<size_t>(fr) * f.ln_mod_ld;
+    const int i = threadIdx.x & 127;
+    const uint4 m = *reinterpret_cast<const uint4*>(mrow + (threadIdx.x < 128 ? f.ln_shift_off : f.ln_scale_off) + i * 8);
+    Epi4Ops e;
+    const int n = warp * 128 + 4 * (threadIdx.x & 31);
+    e.bias = *reinterpret_cast<const uint2*>(g.bias + n);
+    e.gate = *reinterpret_cast<const uint2*>(g.gate + static_cast<size_t>(fr) * g.gate_ld + n);
+    e.res = *reinterpret_cast<const uint2*>(g.res + static_cast<size_t>(tok) * g.ldr + n);
+    *reinterpret_cast<uint4*>(smod + threadIdx.x * 16) = m;
+    return e;
+}
 template <int S>
-__device__ __forceinline__ void skinny_reduce_ln(const SkinnyParams& p, int total, int warp, int lane, uint8_t* srow) {
+__device__ __forceinline__ void skinny_reduce_ln(const SkinnyParams& p, int total, int warp, int lane, uint8_t* smod, uint8_t* srow,
+                                                 Epi4Ops e) {
     const GemmParams& g = p.g;
     const SkinnyFuseParams& f = p.f;
     const int n = warp * 128 + 4 * lane;
@@ -183,24 +246,13 @@ __device__ __forceinline__ void skinny_reduce_ln(const SkinnyParams& p, int tota
         float4 v[S];
 #pragma unroll
         for (int s2 = 0; s2 < S; ++s2) v[s2] = __ldcg(reinterpret_cast<const float4*>(base + (static_cast<size_t>(s2) * total + tok) * 128));
-        uint4 shu[4], scu[4];
-        if (warp == 0) {
-            int fr = tok / g.rows_per_frame;
-            if (g.frame_row != nullptr) fr = g.frame_row[fr];
-            const bf16* mrow = f.ln_mod + static_cast<size_t>(fr) * f.ln_mod_ld;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                shu[c] = *reinterpret_cast<const uint4*>(mrow + f.ln_shift_off + c * 256 + lane * 8);
-                scu[c] = *reinterpret_cast<const uint4*>(mrow + f.ln_scale_off + c * 256 + lane * 8);
-            }
-        }
         float4 acc = v[0];
 #pragma unroll
         for (int s2 = 1; s2 < S; ++s2) { acc.x += v[s2].x; acc.y += v[s2].y; acc.z += v[s2].z; acc.w += v[s2].w; }
-        const uint2 o = skinny_epi4<EPI_BIAS_GATE_RES>(g, tok, n, acc);
+        const uint2 o = skinny_epi4<EPI_BIAS_GATE_RES>(acc, e);
         *reinterpret_cast<uint2*>(g.out + static_cast<size_t>(tok) * g.ldo + n) = o;
         *reinterpret_cast<uint2*>(srow + n * 2) = o;
-        __syncthreads();
+        __syncthreads();                       // the row (and, first time round, the preloaded shift / scale) is in smem
         if (warp == 0) {
             uint4 xu[4];
 #pragma unroll
@@ -209,11 +261,15 @@ __device__ __forceinline__ void skinny_reduce_ln(const SkinnyParams& p, int tota
             float mean, rstd;
             ln_row_stats<4>(xu, x, mean, rstd);
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < 4; ++c) {
+                const uint4 sh = *reinterpret_cast<const uint4*>(smod + (c * 256 + lane * 8) * 2);
+                const uint4 sc = *reinterpret_cast<const uint4*>(smod + 2048 + (c * 256 + lane * 8) * 2);
                 *reinterpret_cast<uint4*>(f.ln_out + static_cast<size_t>(tok) * 1024 + c * 256 + lane * 8) =
-                    ln_modulate_slice(x[c], mean, rstd, shu[c], scu[c]);
+                    ln_modulate_slice(x[c], mean, rstd, sh, sc);
+            }
         }
         __syncthreads();
+        if (tok + static_cast<int>(gridDim.x) < total) e = skinny_ln_preload(p, tok + gridDim.x, warp, smod);
     }
 }
 
@@ -221,16 +277,26 @@ __device__ __forceinline__ void skinny_reduce_ln(const SkinnyParams& p, int tota
 // model/attention.py:41-66): warp w sums the partials of heads 2w and 2w + 1 (row blocks w, 8 + w, 16 + w), lane =
 // one rotary pair, and runs the last-frame temporal attention against the K/V cache with attn_temporal_last_kernel's
 // own code; g.out receives the ATTENTION output [tokens, 1024] (the q/k/v row itself is not needed afterwards).
-template <int S, int TC>
-__device__ __forceinline__ void skinny_reduce_tattn(const SkinnyParams& p, int total, int warp, int lane) {
-    const GemmParams& g = p.g;
+struct TattnPre {
+    uint32_t kc[2][SK_TMAX], vc[2][SK_TMAX];
+};
+__device__ __forceinline__ void skinny_tattn_preload(const SkinnyParams& p, int tok, int warp, int lane, TattnPre& pre) {
     const SkinnyFuseParams& f = p.f;
     constexpr int D = 1024;
-    const int P = f.positions;
-    const float2 cs = f.rot[TC * 32 + lane];
+    const int P = f.positions, tc = f.ctx_frames;
+    const int b = tok / P, pos = tok - b * P;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        const bf16* cache = f.kv_cache + (static_cast<size_t>(b) * tc * P + pos) * (2 * D) + (2 * warp + hh) * 64 + 2 * lane;
+        temporal_cache_load(pre.kc[hh], pre.vc[hh], tc, cache, static_cast<size_t>(P) * 2 * D, D);
+    }
+}
+template <int S, int TC>
+__device__ __forceinline__ void skinny_reduce_tattn(const SkinnyParams& p, int total, int warp, int lane, TattnPre& pre) {
+    const GemmParams& g = p.g;
+    const float2 cs = p.f.rot[TC * 32 + lane];
 #pragma unroll 1
     for (int tok = blockIdx.x; tok < total; tok += gridDim.x) {
-        const int b = tok / P, pos = tok - b * P;
         float2 a[2][3][S];
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh)
@@ -250,11 +316,10 @@ __device__ __forceinline__ void skinny_reduce_tattn(const SkinnyParams& p, int t
                 for (int s2 = 1; s2 < S; ++s2) { acc.x += a[hh][part][s2].x; acc.y += a[hh][part][s2].y; }
                 qkv[part] = make_float2(bf16_round(acc.x), bf16_round(acc.y));       // the Linear's bf16 output
             }
-            const int head = 2 * warp + hh;
-            const bf16* cache = f.kv_cache + (static_cast<size_t>(b) * TC * P + pos) * (2 * D) + head * 64 + 2 * lane;
-            *reinterpret_cast<uint32_t*>(g.out + static_cast<size_t>(tok) * g.ldo + head * 64 + 2 * lane) =
-                temporal_last_core<TC>(qkv[0], qkv[1], qkv[2], cache, static_cast<size_t>(P) * 2 * D, D, cs);
+            *reinterpret_cast<uint32_t*>(g.out + static_cast<size_t>(tok) * g.ldo + (2 * warp + hh) * 64 + 2 * lane) =
+                temporal_last_core<TC>(qkv[0], qkv[1], qkv[2], pre.kc[hh], pre.vc[hh], cs);
         }
+        if (tok + static_cast<int>(gridDim.x) < total) skinny_tattn_preload(p, tok + gridDim.x, warp, lane, pre);
     }
 }
 
@@ -266,10 +331,13 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     const int chunks = p.chunks, tiles = p.tiles, S = p.splits;
     uint8_t* sW = smem;
     uint8_t* sA = smem + chunks * SK_W_CHUNK;
-    uint64_t* bar_w = reinterpret_cast<uint64_t*>(sA + tiles * chunks * SK_A_CHUNK);
+    uint8_t* tail = sA + tiles * chunks * SK_A_CHUNK;
+    uint64_t* bar_w = reinterpret_cast<uint64_t*>(tail);
     uint64_t* bar_a = bar_w + 1;                   // [tiles] (<= 3)
-    uint64_t* bar_acc = bar_w + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 5);
+    uint64_t* bar_acc = bar_w + 6;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 7);
+    uint8_t* smod = tail + 128;                    // fused LayerNorm: shift | scale (4 KB), then one bf16 row (2 KB)
+    uint8_t* srow = smod + 4096;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 128) SK_STAMP(0);                                       // kernel entry
@@ -277,13 +345,14 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     const bool gemm_cta = FUSE == SK_FUSE_NONE || static_cast<int>(blockIdx.x) < p.gemm_ctas;
     const int rb = blockIdx.x / S, split = blockIdx.x - rb * S;
     const int kc0 = split * chunks;
-    const uint32_t tmem_cols = tiles * SK_NT <= 256 ? 256u : 512u;
+    const int total = tiles * SK_NT;
+    const uint32_t tmem_cols = total <= 256 ? 256u : 512u;
 
     if (gemm_cta && warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmW);
         tma_prefetch_desc(&tmA);
         mbar_init(bar_w, 1);
-        for (int t = 0; t < tiles; ++t) mbar_init(&bar_a[t], 1);
+        for (int t = 0; t < 3; ++t) mbar_init(&bar_a[t], 1);
         mbar_init(bar_acc, 1);
         fence_barrier_init();
     }
@@ -296,26 +365,16 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     tcgen05_fence_after();
     const uint32_t tmem_base = gemm_cta ? *tmem_slot : 0u;
     pdl_trigger();
-    if (threadIdx.x == 128) SK_STAMP(1);                                       // set-up done
+    if (!gemm_cta && threadIdx.x == 128) SK_STAMP(1);                          // set-up done
 
-    if (!gemm_cta) {
-        if (warp >= 4) l2_prefetch_share(p.g.prefetch, p.g.prefetch_bytes, (blockIdx.x * 4 + (warp - 4)) * 32 + lane, gridDim.x * 128);
-        pdl_wait();
-    } else if (warp == 0) {
-        if (lane == 0) {
-            mbar_arrive_expect_tx(bar_w, chunks * SK_W_CHUNK);
-            tma_load_3d(sW, &tmW, bar_w, 0, rb * 128, kc0);
-        }
-        pdl_wait();
-    } else if (warp == 1) {
-        pdl_wait();
-        if (lane == 0) {
-            for (int t = 0; t < tiles; ++t) {
-                mbar_arrive_expect_tx(&bar_a[t], chunks * SK_A_CHUNK);
-                tma_load_3d(sA + t * chunks * SK_A_CHUNK, &tmA, &bar_a[t], 0, t * SK_NT, kc0);
-            }
-        }
-    } else if (warp == 2) {
+    if (gemm_cta && warp == 0 && lane == 0) {
+        mbar_arrive_expect_tx(bar_w, chunks * SK_W_CHUNK);
+        tma_load_3d(sW, &tmW, bar_w, 0, rb * 128, kc0);
+        SK_STAMP(1);                                                           // set-up done, W requested
+    }
+    if (warp >= 4)     // idle until the accumulator is ready: pull the NEXT GEMM's weights into L2 meanwhile
+        l2_prefetch_share(p.g.prefetch, p.g.prefetch_bytes, (blockIdx.x * 4 + (warp - 4)) * 32 + lane, gridDim.x * 128);
+    if (gemm_cta && warp == 2) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(128, SK_NT);
             mbar_wait(bar_w, 0);
@@ -335,37 +394,56 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             umma_commit(bar_acc);
         }
         pdl_wait();
-    } else if (warp == 3) {
+    } else {
         pdl_wait();
-    } else if (warp >= 4) {
-        // idle until the accumulator is ready: pull the NEXT GEMM's weights into L2 meanwhile
-        l2_prefetch_share(p.g.prefetch, p.g.prefetch_bytes, (blockIdx.x * 4 + (warp - 4)) * 32 + lane, gridDim.x * 128);
-        pdl_wait();
-        if (S == 1) {
-            const GemmParams& g = p.g;
-            const int q = warp & 3;
-            const int n = rb * 128 + q * 32 + lane;
-            const int total = tiles * SK_NT;
-            float bias_n = 0.f;
-            if (EPI != EPI_STORE) bias_n = __bfloat162float(g.bias[n]);
-            mbar_wait(bar_acc, 0);
-            tcgen05_fence_after();
-            const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-            for (int c = 0; c < total; c += 16) {
-                uint32_t v[16];
-                tmem_ld_32x16(tlane + c, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) skinny_store<EPI>(g, c + i, n, __uint_as_float(v[i]), bias_n);
+        if (gemm_cta && warp == 1 && lane == 0) {
+            for (int t = 0; t < tiles; ++t) {
+                mbar_arrive_expect_tx(&bar_a[t], chunks * SK_A_CHUNK);
+                tma_load_3d(sA + t * chunks * SK_A_CHUNK, &tmA, &bar_a[t], 0, t * SK_NT, kc0);
             }
+        }
+    }
+    // ---- past griddepcontrol.wait: the previous kernels' results are visible.  Start the loads the reduce will need.
+    // Rendezvous group: the S CTAs of this row block (group rb of `counters`, 4 ints each), or, in the fused modes, ALL
+    // CTAs of the grid (group 64).
+    int* const meet = p.counters + 4 * (FUSE == SK_FUSE_NONE ? rb : 64);
+    const int meet_n = FUSE == SK_FUSE_NONE ? S : static_cast<int>(gridDim.x);
+    int sense0 = 0;
+    if (threadIdx.x == 128 && meet_n > 1) sense0 = ld_acquire_gpu(meet + 2);
+    Epi4Ops epre;
+    epre.bias = epre.gate = epre.res = make_uint2(0u, 0u);
+    TattnPre tpre;
+    if (FUSE == SK_FUSE_LN) {
+        if (static_cast<int>(blockIdx.x) < total) epre = skinny_ln_preload(p, blockIdx.x, warp, smod);
+    } else if (FUSE == SK_FUSE_TATTN) {
+        if (static_cast<int>(blockIdx.x) < total) skinny_tattn_preload(p, blockIdx.x, warp, lane, tpre);
+    } else if (EPI != EPI_STORE && S > 1) {
+        epre.bias = *reinterpret_cast<const uint2*>(p.g.bias + rb * 128 + 4 * lane);
+    }
+
+    if (gemm_cta && S == 1 && warp >= 4) {
+        const GemmParams& g = p.g;
+        const int q = warp & 3;
+        const int n = rb * 128 + q * 32 + lane;
+        float bias_n = 0.f;
+        if (EPI != EPI_STORE) bias_n = __bfloat162float(g.bias[n]);
+        mbar_wait(bar_acc, 0);
+        tcgen05_fence_after();
+        const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < total; c += 16) {
+            uint32_t v[16];
+            tmem_ld_32x16(tlane + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) skinny_store<EPI>(g, c + i, n, __uint_as_float(v[i]), bias_n);
         }
     }
     if (S > 1 && gemm_cta) {
         // ---- accumulator -> fp32 partial tile ws[cta][token][128 weight rows], drained by ALL 8 warps: warp w reads the
         // TMEM lane quadrant w % 4, warps 4-7 the first half of the token columns, warps 0-3 (whose producer / MMA roles
         // are over) the second half
-        const int total = tiles * SK_NT, half = total / 2;
+        const int half = total / 2;
         const int q = warp & 3, row = q * 32 + lane;
         mbar_wait(bar_acc, 0);
         tcgen05_fence_after();
@@ -389,96 +467,54 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
         __syncthreads();
         if (threadIdx.x == 128) {
-            int* arrive = p.counters + 2 * rb;
             SK_STAMP(5);                                                       // partials written + fenced
-            atomicAdd(arrive, 1);
-            if (FUSE == SK_FUSE_NONE) {
-                uint32_t spins = 0;
-                while (ld_acquire_gpu(arrive) < S) {
-                    __nanosleep(64);
-                    if (++spins > (1u << 24)) {
-                        printf("gtav: split-K rendezvous timed out (block %d)\n", blockIdx.x);
-                        __trap();
-                    }
-                }
-            }
+            skinny_rendezvous(meet, meet_n, sense0);
         }
+    } else if (FUSE != SK_FUSE_NONE && threadIdx.x == 128) {
+        skinny_rendezvous(meet, meet_n, sense0);                               // reduce-only CTA: nothing to publish
     }
     if (S > 1 && FUSE == SK_FUSE_NONE) {
         // all 8 warps reduce once the rendezvous of the row block has completed
         __syncthreads();
         if (threadIdx.x == 128) SK_STAMP(6);                                   // rendezvous passed
         const GemmParams& g = p.g;
-        const int total = tiles * SK_NT;
         const int lo = split * total / S, hi = (split + 1) * total / S;
         const float* part = p.ws + static_cast<size_t>(rb) * S * total * 128;
         switch (S) {
-            case 2: skinny_reduce<EPI, 2>(g, part, total, lo, hi, warp, lane, rb * 128); break;
-            case 4: skinny_reduce<EPI, 4>(g, part, total, lo, hi, warp, lane, rb * 128); break;
-            case 8: skinny_reduce<EPI, 8>(g, part, total, lo, hi, warp, lane, rb * 128); break;
-            case 16: skinny_reduce<EPI, 16>(g, part, total, lo, hi, warp, lane, rb * 128); break;
+            case 2: skinny_reduce<EPI, 2>(g, part, total, lo, hi, warp, lane, rb * 128, epre.bias); break;
+            case 4: skinny_reduce<EPI, 4>(g, part, total, lo, hi, warp, lane, rb * 128, epre.bias); break;
+            case 8: skinny_reduce<EPI, 8>(g, part, total, lo, hi, warp, lane, rb * 128, epre.bias); break;
+            case 16: skinny_reduce<EPI, 16>(g, part, total, lo, hi, warp, lane, rb * 128, epre.bias); break;
             default: __trap();
         }
-        __syncthreads();
-        if (threadIdx.x == 128) {
-            SK_STAMP(7);                                                       // reduced + stored
-            int* arrive = p.counters + 2 * rb;
-            const int old = atomicAdd(arrive + 1, 1);
-            if (old == S - 1) {                           // everyone of this row block is past the rendezvous
-                arrive[1] = 0;
-                __threadfence();
-                atomicExch(arrive, 0);
-            }
-        }
+        if (threadIdx.x == 128) SK_STAMP(7);                                   // reduced + stored (this warp)
     }
     if (FUSE != SK_FUSE_NONE) {
-        // ---- every CTA waits for ALL row blocks (thread i polls block i's counter), then owns whole token rows
-        const int rbs = p.g.N / 128, total = tiles * SK_NT;
-        if (static_cast<int>(threadIdx.x) < rbs) {
-            const int* arrive = p.counters + 2 * threadIdx.x;
-            uint32_t spins = 0;
-            while (ld_acquire_gpu(arrive) < S) {
-                __nanosleep(64);
-                if (++spins > (1u << 24)) {
-                    printf("gtav: split-K rendezvous timed out (block %d, row block %d)\n", blockIdx.x, threadIdx.x);
-                    __trap();
-                }
-            }
-        }
+        // ---- every CTA has met every other one (thread 128 above): it now owns whole token rows
         __syncthreads();
         if (threadIdx.x == 128) SK_STAMP(6);
         if (FUSE == SK_FUSE_LN) {
             switch (S) {
-                case 2: skinny_reduce_ln<2>(p, total, warp, lane, sW); break;
-                case 4: skinny_reduce_ln<4>(p, total, warp, lane, sW); break;
-                case 8: skinny_reduce_ln<8>(p, total, warp, lane, sW); break;
-                case 16: skinny_reduce_ln<16>(p, total, warp, lane, sW); break;
+                case 2: skinny_reduce_ln<2>(p, total, warp, lane, smod, srow, epre); break;
+                case 4: skinny_reduce_ln<4>(p, total, warp, lane, smod, srow, epre); break;
+                case 8: skinny_reduce_ln<8>(p, total, warp, lane, smod, srow, epre); break;
+                case 16: skinny_reduce_ln<16>(p, total, warp, lane, smod, srow, epre); break;
                 default: __trap();
             }
         } else {
             switch (p.f.ctx_frames) {                                          // S == 4 (checked on the host)
-                case 0: skinny_reduce_tattn<4, 0>(p, total, warp, lane); break;
-                case 1: skinny_reduce_tattn<4, 1>(p, total, warp, lane); break;
-                case 2: skinny_reduce_tattn<4, 2>(p, total, warp, lane); break;
-                case 3: skinny_reduce_tattn<4, 3>(p, total, warp, lane); break;
-                case 4: skinny_reduce_tattn<4, 4>(p, total, warp, lane); break;
-                case 5: skinny_reduce_tattn<4, 5>(p, total, warp, lane); break;
-                case 6: skinny_reduce_tattn<4, 6>(p, total, warp, lane); break;
-                case 7: skinny_reduce_tattn<4, 7>(p, total, warp, lane); break;
+                case 0: skinny_reduce_tattn<4, 0>(p, total, warp, lane, tpre); break;
+                case 1: skinny_reduce_tattn<4, 1>(p, total, warp, lane, tpre); break;
+                case 2: skinny_reduce_tattn<4, 2>(p, total, warp, lane, tpre); break;
+                case 3: skinny_reduce_tattn<4, 3>(p, total, warp, lane, tpre); break;
+                case 4: skinny_reduce_tattn<4, 4>(p, total, warp, lane, tpre); break;
+                case 5: skinny_reduce_tattn<4, 5>(p, total, warp, lane, tpre); break;
+                case 6: skinny_reduce_tattn<4, 6>(p, total, warp, lane, tpre); break;
+                case 7: skinny_reduce_tattn<4, 7>(p, total, warp, lane, tpre); break;
                 default: __trap();
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 128) {
-            SK_STAMP(7);
-            // the last CTA past the rendezvous clears every counter for the next launch (slot 1 = departures)
-            const int old = atomicAdd(p.counters + 1, 1);
-            if (old == static_cast<int>(gridDim.x) - 1) {
-                p.counters[1] = 0;
-                __threadfence();
-                for (int r = 0; r < rbs; ++r) atomicExch(p.counters + 2 * r, 0);
-            }
-        }
+        if (threadIdx.x == 128) SK_STAMP(7);
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -571,7 +607,7 @@ static int skinny_launch(const SkinnyOp* op, cudaStream_t stream) {
     static bool configured = false;
     auto kern = gemm_skinny_kernel<EPI, FUSE>;
     if (!configured) {
-        GTAV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BUDGET + 2048));
+        GTAV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BUDGET + SK_TAIL_BYTES + 1024));
         configured = true;
     }
     SkinnyParams sp;
@@ -580,7 +616,10 @@ static int skinny_launch(const SkinnyOp* op, cudaStream_t stream) {
     sp.trace = op->trace;
     // At least half of the SM's shared memory, so that exactly one CTA of this kernel fits on an SM: the CTAs of a
     // row block wait for each other, and a second CTA on the same SM could block in tcgen05.alloc behind a waiting one.
-    size_t smem = static_cast<size_t>(op->chunks) * (SK_W_CHUNK + op->tiles * SK_A_CHUNK) + 64 + 1024;
+    // (Two CTAs per SM - the next launch starting under the current one - was measured and dropped: TMA loads of an
+    // early-launched CTA that shares its SM with a CTA of the previous kernel do not complete before that CTA exits,
+    // profiles/r01/skinny_coresident_trace.txt.)
+    size_t smem = static_cast<size_t>(op->chunks) * (SK_W_CHUNK + op->tiles * SK_A_CHUNK) + SK_TAIL_BYTES + 1024;
     if (smem < 120 * 1024) smem = 120 * 1024;
     GTAV_CUDA_OK(launch_k(kern, dim3(op->grid), dim3(SK_THREADS), smem, stream, op->tmW, op->tmA, sp));
     return 0;

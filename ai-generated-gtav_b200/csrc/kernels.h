@@ -113,7 +113,7 @@ struct SkinnyOp {
     int grid;         // CTAs launched: (N/128) * splits, or more in the fused modes (reduce-only CTAs)
     int epi, splits, chunks, tiles;
     float* ws;        // fp32 partial-sum workspace, skinny_workspace_bytes(M)
-    int* counters;    // 128 zero-initialised ints (rendezvous counters, self-resetting)
+    int* counters;    // 512 ints, zero before the first launch (rendezvous groups of 4 ints, maintained by the kernel)
     long long* trace; // optional phase time stamps [CTAs][8] (profiling aid), normally null
 };
 bool skinny_supported(int M, int N, int K, int epi);

@@ -235,7 +235,7 @@ def skinny_roofline(dit, B, pk):
     o4 = torch.empty((M, 4 * D), device=dev, dtype=torch.bfloat16)
     bias = torch.zeros(4 * D, device=dev, dtype=torch.bfloat16)
     ws = torch.empty(lib.gtav_gemm_skinny_workspace_bytes(M), dtype=torch.uint8, device=dev)
-    counters = torch.zeros(128, dtype=torch.int32, device=dev)
+    counters = torch.zeros(512, dtype=torch.int32, device=dev)
     halves = _hot_weights(dit)
     shapes = [(0, a1, o3, 3 * D, D, N.EPI_STORE), (1, a1, o1, D, D, N.EPI_BIAS), (3, a1, o4, 4 * D, D, N.EPI_BIAS_GELU_TANH),
               (5, a4, o1, D, 4 * D, N.EPI_BIAS)]

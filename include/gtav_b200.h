@@ -58,8 +58,8 @@ int gtav_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, in
 
 /* The same contract on the weight-streaming kernel used for last-frame steps: M = 144, 288 or 432 rows, N a
  * multiple of 128, K of 64; epilogues STORE / BIAS / BIAS_GELU_TANH / BIAS_GATE_RES (rows_per_frame must be 144).
- * workspace: fp32 scratch of gtav_gemm_skinny_workspace_bytes(M) bytes; counters: 128 ints, zero before the first
- * call (they reset themselves).  splits = 0 lets the library pick the K split. */
+ * workspace: fp32 scratch of gtav_gemm_skinny_workspace_bytes(M) bytes; counters: 512 ints, zero before the first
+ * call (rendezvous state the kernel maintains itself from then on; do not share between concurrent streams).  splits = 0 lets the library pick the K split. */
 size_t gtav_gemm_skinny_workspace_bytes(int M);
 int gtav_gemm_skinny_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
                           int epilogue, const void* bias, const void* res, int ldr, const void* gate, int gate_ld,

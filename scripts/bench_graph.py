@@ -66,7 +66,7 @@ class Bufs:
         self.w_fc1 = [rnd(4 * D, D, scale=1 / 32) for _ in range(NW)]
         self.w_fc2 = [rnd(D, 4 * D, scale=1 / 64) for _ in range(NW)]
         self.ws = torch.empty(lib.gtav_gemm_skinny_workspace_bytes(P), dtype=torch.uint8, device=dev)
-        self.counters = torch.zeros(128, dtype=torch.int32, device=dev)
+        self.counters = torch.zeros(512, dtype=torch.int32, device=dev)
         self.one = torch.zeros(1, dtype=torch.int32, device=dev)
 
 

@@ -53,7 +53,7 @@ def skinny_case(Nn, K, epi=0):
     out = torch.empty((M, Nn), device="cuda", dtype=torch.bfloat16)
     bias = torch.zeros(Nn, device="cuda", dtype=torch.bfloat16)
     ws = torch.empty(lib.gtav_gemm_skinny_workspace_bytes(M), dtype=torch.uint8, device="cuda")
-    counters = torch.zeros(128, dtype=torch.int32, device="cuda")
+    counters = torch.zeros(512, dtype=torch.int32, device="cuda")
     s = N.current_stream()
     for splits in (0, 1, 2, 4, 8, 16):
         def ours():
