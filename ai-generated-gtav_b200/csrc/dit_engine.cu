@@ -2,6 +2,7 @@
 // enqueues the kernel sequence that stands in for DiT.forward (reference model/dit.py:343-376) and
 // SpatioTemporalDiTBlock.forward (model/dit.py:200-225).  No allocation, no host sync: everything is
 // launched on the caller's stream so a whole step can be captured into a CUDA graph.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <new>
@@ -193,8 +194,15 @@ int build_shape(gtav_dit_plan_s* p, Shape* sh, int frames, bool allow_skinny) {
     if (sh->sk[1]) sh->s_out.resize(nh);
     if (sh->sk[2]) sh->s_fc1.resize(nh);
     if (sh->sk[3]) sh->s_fc2.resize(nh);
+    // GTAV_SK_SPLITS="qkv,out,fc1,fc2": K-split override per GEMM kind (0 = the library's choice), for A/B measurements
+    int so[4] = {0, 0, 0, 0};
+    if (const char* e = getenv("GTAV_SK_SPLITS")) sscanf(e, "%d,%d,%d,%d", &so[0], &so[1], &so[2], &so[3]);
+    // to_out of one rollout (N = K = hidden): 4 splits instead of the 16 that would fill the SMs - the split-K exchange
+    // (S x 144 x N fp32 through L2, both ways) costs more than the idle SMs save; measured in the real step
+    // (scripts/bench_graph.py --engine): 16 splits 1.318 ms, 8 splits 1.306 ms, 4 splits 1.297 ms per last-frame step
+    if (so[1] == 0 && M == S) so[1] = 4;
     sh->fuse_ln = sh->sk[1] && sh->sk[3] && fuse_enabled();
-    sh->fuse_tattn = sh->sk[0] && fuse_enabled() && skinny_pick_splits(M, 3 * D, D) == 4 && p->T - 1 <= 7;
+    sh->fuse_tattn = sh->sk[0] && fuse_enabled() && (so[0] > 0 ? so[0] : skinny_pick_splits(M, 3 * D, D)) == 4 && p->T - 1 <= 7;
     const size_t cache_layer = static_cast<size_t>(p->B) * (p->T - 1) * S * 2 * D;
     for (int i = 0; i < nh && rc == 0; ++i) {
         const gtav_dit_half& hw = h->halves[i];
@@ -230,13 +238,13 @@ int build_shape(gtav_dit_plan_s* p, Shape* sh, int frames, bool allow_skinny) {
         f_qkv.positions = S;
         const bool ta = sh->fuse_tattn && (i & 1);
         if (ta) { pq.out = p->att; pq.ldo = D; }
-        if (sh->sk[0]) rc |= skinny_prepare(&sh->s_qkv[i], p->hn, D, static_cast<const bf16*>(hw.qkv_w), D, pq, EPI_STORE, p->sk_ws, p->sk_counters, 0, ta ? &f_qkv : nullptr);
+        if (sh->sk[0]) rc |= skinny_prepare(&sh->s_qkv[i], p->hn, D, static_cast<const bf16*>(hw.qkv_w), D, pq, EPI_STORE, p->sk_ws, p->sk_counters, so[0], ta ? &f_qkv : nullptr);
         else rc |= gemm_prepare(&sh->g_qkv[i], p->hn, D, static_cast<const bf16*>(hw.qkv_w), D, pq, EPI_STORE);
-        if (sh->sk[1]) rc |= skinny_prepare(&sh->s_out[i], p->att, D, static_cast<const bf16*>(hw.out_w), D, po, EPI_BIAS_GATE_RES, p->sk_ws, p->sk_counters, 0, sh->fuse_ln ? &f_out : nullptr);
+        if (sh->sk[1]) rc |= skinny_prepare(&sh->s_out[i], p->att, D, static_cast<const bf16*>(hw.out_w), D, po, EPI_BIAS_GATE_RES, p->sk_ws, p->sk_counters, so[1], sh->fuse_ln ? &f_out : nullptr);
         else rc |= gemm_prepare(&sh->g_out[i], p->att, D, static_cast<const bf16*>(hw.out_w), D, po, EPI_BIAS_GATE_RES);
-        if (sh->sk[2]) rc |= skinny_prepare(&sh->s_fc1[i], p->hn, D, static_cast<const bf16*>(hw.fc1_w), D, p1, EPI_BIAS_GELU_TANH, p->sk_ws, p->sk_counters);
+        if (sh->sk[2]) rc |= skinny_prepare(&sh->s_fc1[i], p->hn, D, static_cast<const bf16*>(hw.fc1_w), D, p1, EPI_BIAS_GELU_TANH, p->sk_ws, p->sk_counters, so[2]);
         else rc |= gemm_prepare(&sh->g_fc1[i], p->hn, D, static_cast<const bf16*>(hw.fc1_w), D, p1, EPI_BIAS_GELU_TANH);
-        if (sh->sk[3]) rc |= skinny_prepare(&sh->s_fc2[i], p->mlp, 4 * D, static_cast<const bf16*>(hw.fc2_w), 4 * D, p2, EPI_BIAS_GATE_RES, p->sk_ws, p->sk_counters, 0, sh->fuse_ln ? &f_fc2 : nullptr);
+        if (sh->sk[3]) rc |= skinny_prepare(&sh->s_fc2[i], p->mlp, 4 * D, static_cast<const bf16*>(hw.fc2_w), 4 * D, p2, EPI_BIAS_GATE_RES, p->sk_ws, p->sk_counters, so[3], sh->fuse_ln ? &f_fc2 : nullptr);
         else rc |= gemm_prepare(&sh->g_fc2[i], p->mlp, 4 * D, static_cast<const bf16*>(hw.fc2_w), 4 * D, p2, EPI_BIAS_GATE_RES);
     }
     rc |= gemm_prepare(&sh->g_final, p->hn, D, static_cast<const bf16*>(w.final_w), D, gp(p->yfin, 64, w.final_b, M, h->out_feat, D), EPI_BIAS);

@@ -291,10 +291,26 @@ __device__ __forceinline__ void skinny_tattn_preload(const SkinnyParams& p, int 
         temporal_cache_load(pre.kc[hh], pre.vc[hh], tc, cache, static_cast<size_t>(P) * 2 * D, D);
     }
 }
-template <int S, int TC>
+// Only the attention core depends on the number of cached frames: dispatch there, so the kernel carries one copy of the
+// partial-sum loads instead of eight (its code size shows up as instruction-fetch stalls in the ncu capture).
+__device__ __forceinline__ uint32_t temporal_last_dispatch(int tc, float2 q, float2 k, float2 v, const uint32_t (&kc)[SK_TMAX],
+                                                           const uint32_t (&vc)[SK_TMAX], float2 cs) {
+    switch (tc) {
+        case 0: return temporal_last_core<0>(q, k, v, kc, vc, cs);
+        case 1: return temporal_last_core<1>(q, k, v, kc, vc, cs);
+        case 2: return temporal_last_core<2>(q, k, v, kc, vc, cs);
+        case 3: return temporal_last_core<3>(q, k, v, kc, vc, cs);
+        case 4: return temporal_last_core<4>(q, k, v, kc, vc, cs);
+        case 5: return temporal_last_core<5>(q, k, v, kc, vc, cs);
+        case 6: return temporal_last_core<6>(q, k, v, kc, vc, cs);
+        default: return temporal_last_core<7>(q, k, v, kc, vc, cs);
+    }
+}
+template <int S>
 __device__ __forceinline__ void skinny_reduce_tattn(const SkinnyParams& p, int total, int warp, int lane, TattnPre& pre) {
     const GemmParams& g = p.g;
-    const float2 cs = p.f.rot[TC * 32 + lane];
+    const int tc = p.f.ctx_frames;
+    const float2 cs = p.f.rot[tc * 32 + lane];
 #pragma unroll 1
     for (int tok = blockIdx.x; tok < total; tok += gridDim.x) {
         float2 a[2][3][S];
@@ -317,7 +333,7 @@ __device__ __forceinline__ void skinny_reduce_tattn(const SkinnyParams& p, int t
                 qkv[part] = make_float2(bf16_round(acc.x), bf16_round(acc.y));       // the Linear's bf16 output
             }
             *reinterpret_cast<uint32_t*>(g.out + static_cast<size_t>(tok) * g.ldo + (2 * warp + hh) * 64 + 2 * lane) =
-                temporal_last_core<TC>(qkv[0], qkv[1], qkv[2], pre.kc[hh], pre.vc[hh], cs);
+                temporal_last_dispatch(tc, qkv[0], qkv[1], qkv[2], pre.kc[hh], pre.vc[hh], cs);
         }
         if (tok + static_cast<int>(gridDim.x) < total) skinny_tattn_preload(p, tok + gridDim.x, warp, lane, pre);
     }
@@ -495,24 +511,13 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         if (threadIdx.x == 128) SK_STAMP(6);
         if (FUSE == SK_FUSE_LN) {
             switch (S) {
-                case 2: skinny_reduce_ln<2>(p, total, warp, lane, smod, srow, epre); break;
                 case 4: skinny_reduce_ln<4>(p, total, warp, lane, smod, srow, epre); break;
                 case 8: skinny_reduce_ln<8>(p, total, warp, lane, smod, srow, epre); break;
                 case 16: skinny_reduce_ln<16>(p, total, warp, lane, smod, srow, epre); break;
                 default: __trap();
             }
         } else {
-            switch (p.f.ctx_frames) {                                          // S == 4 (checked on the host)
-                case 0: skinny_reduce_tattn<4, 0>(p, total, warp, lane, tpre); break;
-                case 1: skinny_reduce_tattn<4, 1>(p, total, warp, lane, tpre); break;
-                case 2: skinny_reduce_tattn<4, 2>(p, total, warp, lane, tpre); break;
-                case 3: skinny_reduce_tattn<4, 3>(p, total, warp, lane, tpre); break;
-                case 4: skinny_reduce_tattn<4, 4>(p, total, warp, lane, tpre); break;
-                case 5: skinny_reduce_tattn<4, 5>(p, total, warp, lane, tpre); break;
-                case 6: skinny_reduce_tattn<4, 6>(p, total, warp, lane, tpre); break;
-                case 7: skinny_reduce_tattn<4, 7>(p, total, warp, lane, tpre); break;
-                default: __trap();
-            }
+            skinny_reduce_tattn<4>(p, total, warp, lane, tpre);                // S == 4, <= 7 cached frames (checked on the host)
         }
         if (threadIdx.x == 128) SK_STAMP(7);
     }
@@ -582,7 +587,7 @@ int skinny_prepare(SkinnyOp* op, const bf16* A, int lda, const bf16* W, int ldw,
     op->grid = rbs * S;
     if (fuse != nullptr && fuse->mode != SK_FUSE_NONE) {
         // per-token reduce: one CTA per token row up to the SM count (all CTAs must be co-resident: they rendezvous)
-        const bool ln_ok = fuse->mode == SK_FUSE_LN && epi == EPI_BIAS_GATE_RES && p.N == 1024 && S > 1 && fuse->ln_out != nullptr &&
+        const bool ln_ok = fuse->mode == SK_FUSE_LN && epi == EPI_BIAS_GATE_RES && p.N == 1024 && S >= 4 && fuse->ln_out != nullptr &&
                            fuse->ln_mod != nullptr && fuse->ln_mod_ld % 8 == 0 && fuse->ln_shift_off % 8 == 0 && fuse->ln_scale_off % 8 == 0;
         const bool ta_ok = fuse->mode == SK_FUSE_TATTN && epi == EPI_STORE && p.N == 3072 && S == 4 && fuse->rot != nullptr &&
                            fuse->ctx_frames >= 0 && fuse->ctx_frames <= 7 && (fuse->ctx_frames == 0 || fuse->kv_cache != nullptr) &&

@@ -89,17 +89,39 @@ class Sampler:
             pass
 
     # ------------------------------------------------------------------ conditioning rows of one frame
-    def _cond_inputs(self, B, T, i, start, actions, dev):
-        """t [rows] int64 and actions [rows, A] for the table layout of gtav_sampler_cond_rows."""
+    def _cond_inputs(self, B, T, act_win, dev):
+        """t [rows] int64 and actions [rows, A] for the table layout of gtav_sampler_cond_rows; act_win: the window's
+        actions [B, T, A] (context frames then the frame being generated) or None."""
         S1 = self.steps + 1
         t_ctx = torch.full((B * (T - 1),), self.stab, dtype=torch.long, device=dev)
         t_last = torch.tensor(self.levels, dtype=torch.long, device=dev).repeat(B)
         t = torch.cat([t_ctx, t_last])
-        if actions is None:
+        if act_win is None:
             return t, None
-        a_ctx = actions[:, start:start + T - 1].reshape(B * (T - 1), -1)
-        a_last = actions[:, start + T - 1].unsqueeze(1).expand(B, S1, -1).reshape(B * S1, -1)
+        a_ctx = act_win[:, : T - 1].reshape(B * (T - 1), -1)
+        a_last = act_win[:, T - 1].unsqueeze(1).expand(B, S1, -1).reshape(B * S1, -1)
         return t, torch.cat([a_ctx, a_last]).to(torch.float32).contiguous()
+
+    # ------------------------------------------------------------------ one generated frame
+    def _denoise_frame(self, ctx_latents, chunk, act_win, stream, steps_limit=None):
+        """ctx_latents [B, T-1, n] fp32 (the window's context frames), chunk [B, n] N(0,1) draws for the new frame,
+        act_win [B, T, A] or None -> the new frame's latent [B, n] (a view of the window buffer: copy it before the
+        next call).  Enqueued on `stream`: clamp, conditioning table, context pass + (steps+1) DDIM steps."""
+        lib = N.load()
+        dev = chunk.device
+        B, n = chunk.shape
+        T = ctx_latents.shape[1] + 1
+        ctx = self._context(B, T, dev)
+        xw = ctx["x_win"]
+        xw[:, : T - 1] = ctx_latents
+        N.check(lib.gtav_noise_clamp(chunk.data_ptr(), xw.data_ptr() + (T - 1) * n * 4, T * n, B, n,
+                                     self.noise_abs_max, stream.cuda_stream), "gtav_noise_clamp")
+        t_rows, a_rows = self._cond_inputs(B, T, act_win, dev)
+        N.check(lib.gtav_dit_conditioning(ctx["plan"], t_rows.data_ptr(), N.ptr(a_rows), stream.cuda_stream),
+                "gtav_dit_conditioning")
+        N.check(lib.gtav_sampler_run_frame(ctx["h"], -1 if steps_limit is None else int(steps_limit),
+                                           stream.cuda_stream), "gtav_sampler_run_frame")
+        return xw[:, T - 1]
 
     # ------------------------------------------------------------------ latents -> latents
     @torch.no_grad()
@@ -125,21 +147,12 @@ class Sampler:
             for i in range(n_prompt, total_frames):
                 start = max(0, i + 1 - self.dit.max_frames)
                 T = i + 1 - start
-                ctx = self._context(B, T, dev)
                 if noise is not None:
                     chunk = noise[:, i - n_prompt].to(device=dev, dtype=torch.float32).reshape(B, n).contiguous()
                 else:
                     chunk = torch.randn((B, n), device=dev, generator=generator)
-                xw = ctx["x_win"]
-                xw[:, : T - 1] = x[:, start:i]
-                N.check(lib.gtav_noise_clamp(chunk.data_ptr(), xw.data_ptr() + (T - 1) * n * 4, T * n, B, n,
-                                             self.noise_abs_max, stream.cuda_stream), "gtav_noise_clamp")
-                t_rows, a_rows = self._cond_inputs(B, T, i, start, actions, dev)
-                N.check(lib.gtav_dit_conditioning(ctx["plan"], t_rows.data_ptr(), N.ptr(a_rows), stream.cuda_stream),
-                        "gtav_dit_conditioning")
-                N.check(lib.gtav_sampler_run_frame(ctx["h"], -1 if steps_limit is None else int(steps_limit),
-                                                   stream.cuda_stream), "gtav_sampler_run_frame")
-                x[:, i] = xw[:, T - 1]
+                act_win = None if actions is None else actions[:, start:start + T]
+                x[:, i] = self._denoise_frame(x[:, start:i], chunk, act_win, stream, steps_limit)
                 if on_frame is not None:
                     on_frame(i, x)
         torch.cuda.current_stream(dev).wait_stream(stream)
@@ -169,3 +182,70 @@ class Sampler:
         lat = self.encode_prompt(prompt_video)
         lat = self.sample_latents(lat, actions, total_frames, noise=noise, generator=generator)
         return self.decode_frames(lat), lat
+
+
+    # ------------------------------------------------------------------ interactive / streaming
+    def stream(self, prompt_video, prompt_actions=None, generator=None):
+        """Frame-at-a-time generation with a per-frame action (the "playable" use of the model): returns a
+        FrameStream whose next(action) denoises ONE new frame against the sliding window and decodes only that frame."""
+        return FrameStream(self, prompt_video, prompt_actions, generator)
+
+
+class FrameStream:
+    """Interactive rollout over a Sampler: the window of the last max_frames - 1 latents (and their actions) is kept on
+    the device; every next() runs clamp -> conditioning -> context pass -> (steps+1) DDIM steps for one frame (one CUDA
+    graph replay) and one single-frame VAE decode.  Same arithmetic as Sampler.generate: with the same noise draws the
+    frames are identical (tests/test_sampler_gpu.py)."""
+
+    def __init__(self, sampler: Sampler, prompt_video, prompt_actions=None, generator=None):
+        N.require_cuda(prompt_video, "prompt_video")
+        self.s = sampler
+        self.dev = prompt_video.device
+        self.generator = generator
+        lat = sampler.encode_prompt(prompt_video)                                  # [B, n, C, h, w]
+        self.B, n_prompt = lat.shape[:2]
+        self.shape = tuple(lat.shape[2:])
+        keep = sampler.dit.max_frames - 1
+        self.window = lat.reshape(self.B, n_prompt, -1).float()[:, -keep:].contiguous() if keep > 0 else lat.new_zeros((self.B, 0, sampler.frame_elems))
+        self.actions = None
+        if prompt_actions is not None:
+            a = prompt_actions.to(self.dev, torch.float32)
+            if a.shape[:2] != (self.B, n_prompt):
+                raise RuntimeError(f"prompt_actions must be [B={self.B}, n_prompt={n_prompt}, A], got {tuple(a.shape)}")
+            self.actions = a[:, -keep:].contiguous() if keep > 0 else a[:, :0]
+        self.frames_generated = 0
+        if sampler.use_graph and sampler._stream is None:
+            sampler._stream = torch.cuda.Stream(device=self.dev)
+
+    @torch.no_grad()
+    def next(self, action=None, noise=None, decode=True):
+        """action: [B, A] (or [A]) for the frame to generate - required iff the stream was opened with prompt_actions;
+        noise: optional [B, C, h, w] N(0,1) draws.  Returns (uint8 frame [B, H, W, 3] or None, latent [B, C, h, w])."""
+        s, dev, B = self.s, self.dev, self.B
+        n = s.frame_elems
+        if (action is None) != (self.actions is None):
+            raise RuntimeError("FrameStream.next: pass an action iff the stream was opened with prompt_actions")
+        act_win = None
+        if action is not None:
+            a = action.to(dev, torch.float32).reshape(-1, action.shape[-1])
+            if a.shape[0] == 1 and B > 1:
+                a = a.expand(B, -1)
+            act_win = torch.cat([self.actions, a.unsqueeze(1)], dim=1)
+        if noise is not None:
+            chunk = noise.to(device=dev, dtype=torch.float32).reshape(B, n).contiguous()
+        else:
+            chunk = torch.randn((B, n), device=dev, generator=self.generator)
+        stream = s._stream if s.use_graph else torch.cuda.current_stream(dev)
+        stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.device(dev), torch.cuda.stream(stream):
+            new = s._denoise_frame(self.window, chunk, act_win, stream).clone()
+        torch.cuda.current_stream(dev).wait_stream(stream)
+        keep = s.dit.max_frames - 1
+        if keep > 0:
+            self.window = torch.cat([self.window, new.unsqueeze(1)], dim=1)[:, -keep:].contiguous()
+            if act_win is not None:
+                self.actions = act_win[:, -keep:].contiguous()
+        self.frames_generated += 1
+        latent = new.reshape(B, *self.shape)
+        frame = s.decode_frames(latent.unsqueeze(1))[:, 0] if decode else None
+        return frame, latent

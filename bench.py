@@ -133,7 +133,12 @@ def synthetic_prompt(B, n):
 def launches_per_rollout(wl, algorithm, depth=16, enc=6, dec=12):
     """Kernels of OURS launched per rollout batch (mirrors dit_engine.cu / vae_engine.cu / sampler.cu)."""
     backbone = 2 + 2 * depth * 7 + 3                           # patchify, patch GEMM, 7 per half, final LN/GEMM/unpatchify
-    step = 1 + backbone + 1                                    # step_prep, backbone (window or last frame), ddim
+    last = backbone
+    if algorithm == "cached" and wl["B"] == 1 and os.environ.get("GTAV_FUSE", "1") != "0" and os.environ.get("GTAV_SKINNY", "1") != "0":
+        # one rollout: LayerNorm + modulate and the temporal attention run inside the weight-streaming GEMMs' reduce
+        # (dit_engine.cu: fuse_ln / fuse_tattn) - first LN, then 5 kernels per spatial half and 4 per temporal half
+        last = 2 + 1 + depth * (5 + 4) + 2
+    step = 1 + (last if algorithm == "cached" else backbone) + 1   # step_prep, backbone (window or last frame), ddim
     gen = wl["total"] - wl["n_prompt"]
     context = (2 + 2 * depth * 7) if algorithm == "cached" else 0
     per_frame = 1 + 1 + 4 + context + (wl["steps"] + 1) * step  # clamp, set_int, conditioning(4), context pass, steps
@@ -455,7 +460,7 @@ def main():
                                  step_tflops=round(step_dense_gf / ms_dense, 1), frac=round(step_dense_gf / ms_dense / pk["tf"], 4),
                                  gemm_roofline=gemm_roofline(dit, B, pk),
                                  note="every step recomputes the whole window; DiT steps only (no VAE), 1 generated frame timed")
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:             # rank 0 at N = 1 only
             line["cpu_baseline"] = cpu_baseline(wl)
         print(json.dumps(line), flush=True)
     if dist is not None:

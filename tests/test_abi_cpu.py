@@ -126,3 +126,28 @@ def test_schedule_dropin_matches_oracle():
     from oracle.reference_port import sigmoid_beta_schedule as ref
     assert torch.equal(sigmoid_beta_schedule(1000), ref(1000))
     assert torch.equal(sigmoid_beta_schedule(50, start=-2, end=4, tau=0.9), ref(50, start=-2.0, end=4.0, tau=0.9))
+
+
+def test_trainer_inference_contract_cpu():
+    """The inference-side DiffusionTrainer surface (reference train_dit.py:128-157, 288-552) exists with the reference's
+    defaults; nothing here touches the GPU."""
+    import dataclasses
+    import inspect
+    from gtav_b200.train_dit import DiffusionTrainer, TrainingConfig, denoise_step
+    cfg = TrainingConfig()
+    assert (cfg.ddim_noise_steps, cfg.ddim_noise_steps_inference, cfg.ctx_max_noise_idx, cfg.noise_abs_max, cfg.n_prompt_frames,
+            cfg.use_action_conditioning, cfg.model_name, cfg.seed) == (16, 16, 3, 20.0, 1, True, "dit", 42)
+    assert TrainingConfig.from_dict(dict(ddim_noise_steps=8, learning_rate=1e-5)).ddim_noise_steps == 8   # unknown keys ignored
+    for name in ("register_buffers", "encode_frames", "decode_frames", "predict", "predict_noise", "train"):
+        assert callable(getattr(DiffusionTrainer, name))
+    assert list(inspect.signature(DiffusionTrainer.decode_frames).parameters)[:3] == ["self", "frames", "num_frames"]
+    assert list(inspect.signature(DiffusionTrainer.predict).parameters)[:5] == ["self", "test_loader", "epoch", "global_step", "num_frames"]
+    assert list(inspect.signature(denoise_step).parameters) == ["dit_model", "x_noisy", "actions", "noise_idx", "stabilization_level",
+                                                                "noise_range", "alphas_cumprod", "start_frame", "dtype"]
+
+
+def test_frame_stream_contract_cpu():
+    from gtav_b200.sampler import FrameStream, Sampler
+    import inspect
+    assert list(inspect.signature(FrameStream.next).parameters) == ["self", "action", "noise", "decode"]
+    assert callable(Sampler.stream)

@@ -132,3 +132,68 @@ def test_sampler_without_actions_and_growing_window(models):
     err = (x.cpu() - ref).abs()
     print(f"growing window vs bf16 oracle: max-abs {float(err.max()):.4f} mean-abs {float(err.mean()):.5f}")
     assert float(err.max()) < 1e-1 and float(err.mean()) < 1e-2
+
+
+def test_frame_stream_equals_batch_generate(models):
+    """Interactive frame-at-a-time generation (per-frame action, single-frame decode) == Sampler.generate on the same
+    noise draws and the same action sequence: latents bit for bit, decoded frames identical."""
+    from gtav_b200.sampler import Sampler
+    dit, vae = models
+    steps, total, n_prompt, B = 3, 8, 2, 2
+    video = dummy_prompt(5)[None, :n_prompt].expand(B, -1, -1, -1, -1).contiguous().cuda()
+    noise = torch.randn((B, total - n_prompt, 16, 18, 32), generator=torch.Generator().manual_seed(16)).cuda()
+    acts = torch.zeros(B, total, 25, device="cuda")
+    acts[0, :, 3] = 1.0
+    acts[1, :, 5] = 1.0
+    acts[:, 4:, 9] = 1.0
+    s = Sampler(dit, vae, noise_steps=steps)
+    frames, lat = s.generate(video, acts, total, noise=noise)
+    st = s.stream(video, prompt_actions=acts[:, :n_prompt])
+    for i in range(n_prompt, total):
+        f, z = st.next(action=acts[:, i], noise=noise[:, i - n_prompt])
+        assert torch.equal(z, lat[:, i]), f"frame {i}: streamed latent differs from the batch rollout"
+        assert f.shape == (B, 360, 640, 3) and f.dtype == torch.uint8
+        assert torch.equal(f, frames[:, i]), f"frame {i}: streamed pixels differ"
+    assert st.frames_generated == total - n_prompt
+    with pytest.raises(RuntimeError, match="action"):
+        st.next()                                                   # opened with actions: every frame needs one
+    # unconditioned stream, noise from the generator
+    st2 = s.stream(video, generator=torch.Generator(device="cuda").manual_seed(3))
+    f, z = st2.next()
+    assert torch.isfinite(z).all() and f.shape == (B, 360, 640, 3)
+
+
+def test_trainer_inference_methods(models):
+    """DiffusionTrainer's inference side (train_dit.py:329-552 of the reference) on the drop-in modules:
+    encode/decode against the CPU oracle, predict == its own literal stepwise loop, predict_noise runs the window."""
+    from gtav_b200.train_dit import DiffusionTrainer, TrainingConfig
+    dit, vae = models
+    c = ROLLOUT
+    cfg = TrainingConfig(ddim_noise_steps=16, ddim_noise_steps_inference=3, n_prompt_frames=2, use_action_conditioning=True)
+    tr = DiffusionTrainer(cfg, dit, vae)
+    assert int(tr.stabilization_level) == 62 and tr.noise_range_inference.tolist() == [0, 333, 666, 999]
+    assert tuple(tr.alphas_cumprod.shape) == (1000, 1, 1, 1)
+    video = dummy_prompt(5)[None].cuda()                                        # [1, 5, 3, 360, 640]
+    loader = [dict(video=video, actions=w_key_actions(1, 5).cuda())]
+    lat = tr.encode_frames(video[:, :2])
+    vsd = make_vae_state(VAEConfig(enc_depth=c["enc_depth"], dec_depth=c["dec_depth"]), seed=0)
+    vcfg = VAEConfig(enc_depth=c["enc_depth"], dec_depth=c["dec_depth"])
+    ref = rp.vae_encode_mean(vsd, vcfg, video[0, :2].cpu() * 2 - 1) * 0.07843137255
+    ref = ref.reshape(1, 2, 18, 32, 16).permute(0, 1, 4, 2, 3)
+    assert float((lat.float().cpu() - ref).abs().max()) < 1e-2
+    pix = tr.decode_frames(lat, 2)
+    assert pix.shape == (1, 2, 360, 640, 3) and pix.dtype == torch.uint8
+    with pytest.raises(RuntimeError, match="num_frames"):
+        tr.decode_frames(lat, 3)
+    g1 = torch.Generator(device="cuda").manual_seed(11)
+    g2 = torch.Generator(device="cuda").manual_seed(11)
+    pa, xa = tr.predict(loader, num_frames=6, generator=g1)
+    pb, xb = tr.predict(loader, num_frames=6, generator=g2, stepwise=True)
+    assert pa.shape == (1, 6, 360, 640, 3)
+    err = float((xa.float() - xb.float()).abs().max())
+    print(f"trainer.predict: Sampler vs literal stepwise loop max-abs {err:.5f}")
+    assert err <= 5e-2                                                          # frame cache + skinny GEMM vs dense window
+    x_noisy, latents, v = tr.predict_noise(loader, generator=torch.Generator(device="cuda").manual_seed(12))
+    assert x_noisy.shape == latents.shape == (1, 5, 16, 18, 32) and torch.isfinite(x_noisy).all() and v.shape == (1, 5, 16, 18, 32)
+    with pytest.raises(NotImplementedError):
+        tr.train()
