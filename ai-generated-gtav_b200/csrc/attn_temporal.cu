@@ -40,8 +40,8 @@ attn_temporal_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int B
         const float2 cs = rot[t * 32 + lane];
         const float2 qx = unpack_bf16x2(qu), kx = unpack_bf16x2(ku);
         // rotate in fp32, round once to bf16 (apply_rotary_emb casts back to the input dtype)
-        q[t] = make_float2(bf16_round(qx.x * cs.x - qx.y * cs.y), bf16_round(qx.y * cs.x + qx.x * cs.y));
-        k[t] = make_float2(bf16_round(kx.x * cs.x - kx.y * cs.y), bf16_round(kx.y * cs.x + kx.x * cs.y));
+        q[t] = rotary_pair_rn(qx, cs);
+        k[t] = rotary_pair_rn(kx, cs);
         v[t] = unpack_bf16x2(vu);
         if (kv_cache != nullptr) {
             // rotated K (already rounded to bf16) and V of every frame, row-for-row like qkv: [row][k | v][D]
@@ -56,22 +56,22 @@ attn_temporal_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int B
         float m = -INFINITY;
 #pragma unroll
         for (int j = 0; j <= i; ++j) {
-            s[j] = warp_sum(q[i].x * k[j].x + q[i].y * k[j].y) * 0.125f;
+            s[j] = __fmul_rn(warp_sum(dot_pair_rn(q[i], k[j])), 0.125f);
             m = fmaxf(m, s[j]);
         }
         float l = 0.f;
 #pragma unroll
         for (int j = 0; j <= i; ++j) {
-            s[j] = __expf(s[j] - m);
-            l += s[j];
+            s[j] = __expf(__fsub_rn(s[j], m));
+            l = __fadd_rn(l, s[j]);
         }
-        const float inv = 1.0f / l;
+        const float inv = __frcp_rn(l);
         float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j <= i; ++j) {
-            const float p = bf16_round(s[j] * inv);          // probabilities enter P@V as bf16
-            acc.x += p * v[j].x;
-            acc.y += p * v[j].y;
+            const float p = bf16_round(__fmul_rn(s[j], inv));   // probabilities enter P@V as bf16
+            acc.x = __fmaf_rn(p, v[j].x, acc.x);
+            acc.y = __fmaf_rn(p, v[j].y, acc.y);
         }
         const size_t row = (static_cast<size_t>(b) * T + i) * P + pos;
         *reinterpret_cast<uint32_t*>(out + row * D + head * 64 + 2 * lane) = pack_bf16x2(acc.x, acc.y);
@@ -105,7 +105,7 @@ attn_temporal_last_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, 
     const float2 vx = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(base + 2 * D));
     uint32_t kc[TC > 0 ? TC : 1], vc[TC > 0 ? TC : 1];
     temporal_cache_load(kc, vc, TC, cache, static_cast<size_t>(P) * 2 * D, D);
-    *reinterpret_cast<uint32_t*>(out + qrow * D + head * 64 + 2 * lane) = temporal_last_core<TC>(qx, kx, vx, kc, vc, rot[TC * 32 + lane]);
+    *reinterpret_cast<uint32_t*>(out + qrow * D + head * 64 + 2 * lane) = temporal_last_core(TC, qx, kx, vx, kc, vc, rot[TC * 32 + lane]);
 }
 
 int launch_attention_temporal_last(const bf16* qkv, bf16* out, int B, int ctx_frames, int positions, int heads,

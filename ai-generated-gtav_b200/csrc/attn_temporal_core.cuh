@@ -8,6 +8,15 @@
 
 namespace gtav {
 
+// Every fp32 operation below is an explicit round-to-nearest intrinsic: the same source compiled into different kernels
+// must not be contracted into FMAs differently (the fused and the stand-alone paths are tested for equal bits), and
+// the rotation is the reference's unfused t * cos + rotate_half(t) * sin (rotary_embedding_torch.py:46-73).
+__device__ __forceinline__ float2 rotary_pair_rn(float2 x, float2 cs) {
+    return make_float2(bf16_round(__fsub_rn(__fmul_rn(x.x, cs.x), __fmul_rn(x.y, cs.y))),
+                       bf16_round(__fadd_rn(__fmul_rn(x.y, cs.x), __fmul_rn(x.x, cs.y))));
+}
+__device__ __forceinline__ float dot_pair_rn(float2 a, float2 b) { return __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y)); }
+
 // This lane's pairs of the cached rotated K and V of context frames 0 .. tc-1 (packed bf16x2), TMAX >= tc.
 // cache: kv_cache + (first context row of this (b, pos)) * 2D + head*64 + 2*lane, consecutive frames frame_stride
 // elements apart.  Separate from the core so that callers can issue the loads early.
@@ -27,44 +36,46 @@ __device__ __forceinline__ void temporal_cache_load(uint32_t (&kc)[TMAX], uint32
 }
 
 // qx, kx, vx: this lane's un-rotated q / k pair and v pair of the last frame (bf16 values as floats); kc / vc: the
-// first TC entries are the cached context pairs (temporal_cache_load); cs: (cos, sin) of window position TC for this
-// lane's pair.  Returns the packed bf16 output pair.
-template <int TC, int TMAX>
-__device__ __forceinline__ uint32_t temporal_last_core(float2 qx, float2 kx, float2 vx, const uint32_t (&kc)[TMAX],
+// first tc entries are the cached context pairs (temporal_cache_load); cs: (cos, sin) of window position tc for this
+// lane's pair.  tc (<= TMAX, warp-uniform) is a run-time value: the loops are unrolled to TMAX + 1 keys and predicated,
+// which executes exactly the operations, in the order, of a loop over the tc + 1 real keys - one copy of the code for
+// every window length (a compile-time tc folds the predicates away).  Returns the packed bf16 output pair.
+template <int TMAX>
+__device__ __forceinline__ uint32_t temporal_last_core(int tc, float2 qx, float2 kx, float2 vx, const uint32_t (&kc)[TMAX],
                                                        const uint32_t (&vc)[TMAX], float2 cs) {
-    static_assert(TC <= TMAX, "context frames exceed the cache registers");
-    float2 k[TC + 1], v[TC + 1];
-#pragma unroll
-    for (int t = 0; t < TC; ++t) {
-        k[t] = unpack_bf16x2(kc[t]);
-        v[t] = unpack_bf16x2(vc[t]);
-    }
     // rotate in fp32, round once to bf16 (apply_rotary_emb casts back to the input dtype)
-    const float2 q = make_float2(bf16_round(qx.x * cs.x - qx.y * cs.y), bf16_round(qx.y * cs.x + qx.x * cs.y));
-    k[TC] = make_float2(bf16_round(kx.x * cs.x - kx.y * cs.y), bf16_round(kx.y * cs.x + kx.x * cs.y));
-    v[TC] = vx;
-
-    float s[TC + 1];
+    const float2 q = rotary_pair_rn(qx, cs);
+    const float2 kn = rotary_pair_rn(kx, cs);
+    float s[TMAX + 1];
     float m = -INFINITY;
 #pragma unroll
-    for (int j = 0; j <= TC; ++j) {
-        s[j] = warp_sum(q.x * k[j].x + q.y * k[j].y) * 0.125f;
-        m = fmaxf(m, s[j]);
+    for (int j = 0; j <= TMAX; ++j) {
+        s[j] = 0.f;
+        if (j <= tc) {                                       // key j: cached frame j, or (j == tc) the frame's own
+            float2 k = kn;
+            if (j < TMAX && j < tc) k = unpack_bf16x2(kc[j < TMAX ? j : 0]);
+            s[j] = __fmul_rn(warp_sum(dot_pair_rn(q, k)), 0.125f);
+            m = fmaxf(m, s[j]);
+        }
     }
     float l = 0.f;
 #pragma unroll
-    for (int j = 0; j <= TC; ++j) {
-        s[j] = __expf(s[j] - m);
-        l += s[j];
-    }
-    const float inv = 1.0f / l;
+    for (int j = 0; j <= TMAX; ++j)
+        if (j <= tc) {
+            s[j] = __expf(__fsub_rn(s[j], m));
+            l = __fadd_rn(l, s[j]);
+        }
+    const float inv = __frcp_rn(l);
     float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j <= TC; ++j) {
-        const float p = bf16_round(s[j] * inv);              // probabilities enter P@V as bf16
-        acc.x += p * v[j].x;
-        acc.y += p * v[j].y;
-    }
+    for (int j = 0; j <= TMAX; ++j)
+        if (j <= tc) {
+            float2 v = vx;
+            if (j < TMAX && j < tc) v = unpack_bf16x2(vc[j < TMAX ? j : 0]);
+            const float p = bf16_round(__fmul_rn(s[j], inv));   // probabilities enter P@V as bf16
+            acc.x = __fmaf_rn(p, v.x, acc.x);
+            acc.y = __fmaf_rn(p, v.y, acc.y);
+        }
     return pack_bf16x2(acc.x, acc.y);
 }
 

@@ -234,21 +234,33 @@ __device__ __forceinline__ Epi4Ops skinny_ln_preload(const SkinnyParams& p, int 
     *reinterpret_cast<uint4*>(smod + threadIdx.x * 16) = m;
     return e;
 }
+// Sum of the S partials at p0, p0 + stride, ... in split order, all loads in flight together.
 template <int S>
-__device__ __forceinline__ void skinny_reduce_ln(const SkinnyParams& p, int total, int warp, int lane, uint8_t* smod, uint8_t* srow,
-                                                 Epi4Ops e) {
+__device__ __forceinline__ float4 skinny_sum4(const float* p0, size_t stride) {
+    float4 v[S];
+#pragma unroll
+    for (int s2 = 0; s2 < S; ++s2) v[s2] = __ldcg(reinterpret_cast<const float4*>(p0 + s2 * stride));
+    float4 acc = v[0];
+#pragma unroll
+    for (int s2 = 1; s2 < S; ++s2) { acc.x += v[s2].x; acc.y += v[s2].y; acc.z += v[s2].z; acc.w += v[s2].w; }
+    return acc;
+}
+__device__ __forceinline__ void skinny_reduce_ln(const SkinnyParams& p, int S, int total, int warp, int lane, uint8_t* smod,
+                                                 uint8_t* srow, Epi4Ops e) {
     const GemmParams& g = p.g;
     const SkinnyFuseParams& f = p.f;
     const int n = warp * 128 + 4 * lane;
     const float* base = p.ws + static_cast<size_t>(warp) * S * total * 128 + 4 * lane;
+    const size_t stride = static_cast<size_t>(total) * 128;
 #pragma unroll 1
     for (int tok = blockIdx.x; tok < total; tok += gridDim.x) {
-        float4 v[S];
-#pragma unroll
-        for (int s2 = 0; s2 < S; ++s2) v[s2] = __ldcg(reinterpret_cast<const float4*>(base + (static_cast<size_t>(s2) * total + tok) * 128));
-        float4 acc = v[0];
-#pragma unroll
-        for (int s2 = 1; s2 < S; ++s2) { acc.x += v[s2].x; acc.y += v[s2].y; acc.z += v[s2].z; acc.w += v[s2].w; }
+        const float* p0 = base + static_cast<size_t>(tok) * 128;
+        float4 acc;
+        switch (S) {                           // only the partial-sum loads depend on S: one copy of everything else
+            case 4: acc = skinny_sum4<4>(p0, stride); break;
+            case 8: acc = skinny_sum4<8>(p0, stride); break;
+            default: acc = skinny_sum4<16>(p0, stride); break;
+        }
         const uint2 o = skinny_epi4<EPI_BIAS_GATE_RES>(acc, e);
         *reinterpret_cast<uint2*>(g.out + static_cast<size_t>(tok) * g.ldo + n) = o;
         *reinterpret_cast<uint2*>(srow + n * 2) = o;
@@ -291,21 +303,6 @@ __device__ __forceinline__ void skinny_tattn_preload(const SkinnyParams& p, int 
         temporal_cache_load(pre.kc[hh], pre.vc[hh], tc, cache, static_cast<size_t>(P) * 2 * D, D);
     }
 }
-// Only the attention core depends on the number of cached frames: dispatch there, so the kernel carries one copy of the
-// partial-sum loads instead of eight (its code size shows up as instruction-fetch stalls in the ncu capture).
-__device__ __forceinline__ uint32_t temporal_last_dispatch(int tc, float2 q, float2 k, float2 v, const uint32_t (&kc)[SK_TMAX],
-                                                           const uint32_t (&vc)[SK_TMAX], float2 cs) {
-    switch (tc) {
-        case 0: return temporal_last_core<0>(q, k, v, kc, vc, cs);
-        case 1: return temporal_last_core<1>(q, k, v, kc, vc, cs);
-        case 2: return temporal_last_core<2>(q, k, v, kc, vc, cs);
-        case 3: return temporal_last_core<3>(q, k, v, kc, vc, cs);
-        case 4: return temporal_last_core<4>(q, k, v, kc, vc, cs);
-        case 5: return temporal_last_core<5>(q, k, v, kc, vc, cs);
-        case 6: return temporal_last_core<6>(q, k, v, kc, vc, cs);
-        default: return temporal_last_core<7>(q, k, v, kc, vc, cs);
-    }
-}
 template <int S>
 __device__ __forceinline__ void skinny_reduce_tattn(const SkinnyParams& p, int total, int warp, int lane, TattnPre& pre) {
     const GemmParams& g = p.g;
@@ -333,7 +330,7 @@ __device__ __forceinline__ void skinny_reduce_tattn(const SkinnyParams& p, int t
                 qkv[part] = make_float2(bf16_round(acc.x), bf16_round(acc.y));       // the Linear's bf16 output
             }
             *reinterpret_cast<uint32_t*>(g.out + static_cast<size_t>(tok) * g.ldo + (2 * warp + hh) * 64 + 2 * lane) =
-                temporal_last_dispatch(tc, qkv[0], qkv[1], qkv[2], pre.kc[hh], pre.vc[hh], cs);
+                temporal_last_core(tc, qkv[0], qkv[1], qkv[2], pre.kc[hh], pre.vc[hh], cs);
         }
         if (tok + static_cast<int>(gridDim.x) < total) skinny_tattn_preload(p, tok + gridDim.x, warp, lane, pre);
     }
@@ -437,7 +434,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         epre.bias = *reinterpret_cast<const uint2*>(p.g.bias + rb * 128 + 4 * lane);
     }
 
-    if (gemm_cta && S == 1 && warp >= 4) {
+    if (FUSE == SK_FUSE_NONE && S == 1 && warp >= 4) {
         const GemmParams& g = p.g;
         const int q = warp & 3;
         const int n = rb * 128 + q * 32 + lane;
@@ -510,12 +507,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         __syncthreads();
         if (threadIdx.x == 128) SK_STAMP(6);
         if (FUSE == SK_FUSE_LN) {
-            switch (S) {
-                case 4: skinny_reduce_ln<4>(p, total, warp, lane, smod, srow, epre); break;
-                case 8: skinny_reduce_ln<8>(p, total, warp, lane, smod, srow, epre); break;
-                case 16: skinny_reduce_ln<16>(p, total, warp, lane, smod, srow, epre); break;
-                default: __trap();
-            }
+            skinny_reduce_ln(p, S, total, warp, lane, smod, srow, epre);       // S in {4, 8, 16} (checked on the host)
         } else {
             skinny_reduce_tattn<4>(p, total, warp, lane, tpre);                // S == 4, <= 7 cached frames (checked on the host)
         }
@@ -587,7 +579,7 @@ int skinny_prepare(SkinnyOp* op, const bf16* A, int lda, const bf16* W, int ldw,
     op->grid = rbs * S;
     if (fuse != nullptr && fuse->mode != SK_FUSE_NONE) {
         // per-token reduce: one CTA per token row up to the SM count (all CTAs must be co-resident: they rendezvous)
-        const bool ln_ok = fuse->mode == SK_FUSE_LN && epi == EPI_BIAS_GATE_RES && p.N == 1024 && S >= 4 && fuse->ln_out != nullptr &&
+        const bool ln_ok = fuse->mode == SK_FUSE_LN && epi == EPI_BIAS_GATE_RES && p.N == 1024 && (S == 4 || S == 8 || S == 16) && fuse->ln_out != nullptr &&
                            fuse->ln_mod != nullptr && fuse->ln_mod_ld % 8 == 0 && fuse->ln_shift_off % 8 == 0 && fuse->ln_scale_off % 8 == 0;
         const bool ta_ok = fuse->mode == SK_FUSE_TATTN && epi == EPI_STORE && p.N == 3072 && S == 4 && fuse->rot != nullptr &&
                            fuse->ctx_frames >= 0 && fuse->ctx_frames <= 7 && (fuse->ctx_frames == 0 || fuse->kv_cache != nullptr) &&

@@ -7,6 +7,9 @@
 
 namespace gtav {
 
+// Explicit round-to-nearest intrinsics throughout: the same source inlined into different kernels must produce the
+// same bits (no compiler-chosen FMA contraction), and LN(x) * (1 + scale) + shift is evaluated unfused like the
+// reference's separate fp32 tensor ops (model/dit.py:26-27).
 // xu: this lane's 8-element slices of the row (chunk c covers features c*256 + lane*8 .. +7).
 // modulate: shu / scu = the same slices of the shift / scale vectors (bf16).
 template <int CHUNKS>
@@ -21,19 +24,19 @@ __device__ __forceinline__ void ln_row_stats(const uint4 (&xu)[CHUNKS], float (&
             float2 f = unpack_bf16x2(uw[j]);
             v[c][2 * j] = f.x;
             v[c][2 * j + 1] = f.y;
-            sum += f.x + f.y;
+            sum = __fadd_rn(sum, __fadd_rn(f.x, f.y));
         }
     }
-    mean = warp_sum(sum) * (1.0f / D);
+    mean = __fmul_rn(warp_sum(sum), 1.0f / D);
     float sq = 0.f;
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float d = v[c][j] - mean;
-            sq += d * d;
+            const float d = __fsub_rn(v[c][j], mean);
+            sq = __fmaf_rn(d, d, sq);
         }
-    rstd = rsqrtf(warp_sum(sq) * (1.0f / D) + 1e-6f);
+    rstd = rsqrtf(__fadd_rn(__fmul_rn(warp_sum(sq), 1.0f / D), 1e-6f));
 }
 
 // y = LN(x) * bf16(1 + bf16(scale + 1e-6)) + shift for one 8-element slice -> packed bf16
@@ -44,10 +47,10 @@ __device__ __forceinline__ uint4 ln_modulate_slice(const float (&v)[8], float me
     for (int j = 0; j < 4; ++j) {
         const float2 s2 = unpack_bf16x2(shw[j]), c2 = unpack_bf16x2(scw[j]);
         // scale + 1e-6 and 1 + scale are bf16 tensor ops in the reference (model/dit.py:26-27)
-        const float m0 = bf16_round(1.0f + bf16_round(c2.x + 1e-6f));
-        const float m1 = bf16_round(1.0f + bf16_round(c2.y + 1e-6f));
-        y[2 * j] = (v[2 * j] - mean) * rstd * m0 + s2.x;
-        y[2 * j + 1] = (v[2 * j + 1] - mean) * rstd * m1 + s2.y;
+        const float m0 = bf16_round(__fadd_rn(1.0f, bf16_round(__fadd_rn(c2.x, 1e-6f))));
+        const float m1 = bf16_round(__fadd_rn(1.0f, bf16_round(__fadd_rn(c2.y, 1e-6f))));
+        y[2 * j] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v[2 * j], mean), rstd), m0), s2.x);
+        y[2 * j + 1] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v[2 * j + 1], mean), rstd), m1), s2.y);
     }
     uint4 o;
     o.x = pack_bf16x2(y[0], y[1]);

@@ -19,19 +19,29 @@ ln_rows_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int M, const 
                int shift_off, int scale_off, const int* __restrict__ frame_row, int rows_per_frame,
                const float* __restrict__ w, const float* __restrict__ b) {
     constexpr int D = CHUNKS * 256;
+    // shift | scale of the CTA's frame, staged once per CTA with cp.async right after the dependency wait: as plain
+    // loads ptxas sinks them to their uses after the statistics (three exposed round trips instead of one)
+    __shared__ __align__(16) uint8_t smod[2 * D * 2];
     pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
-    if (row >= M) return;
-    const bf16* xr = x + static_cast<size_t>(row) * D;
-    // issue every global load of the row up front (x, and the shift / scale vectors whose address hangs off
-    // frame_row): the kernel is a chain of memory round trips otherwise
+    const bool staged = !AFFINE && CHUNKS == 4 && rows_per_frame % LN_WARPS == 0;   // all rows of the CTA share a frame
+    if (staged) {
+        int f = (blockIdx.x * LN_WARPS) / rows_per_frame;
+        if (frame_row != nullptr) f = frame_row[f];
+        const int i = threadIdx.x & 127;
+        const bf16* src = mod + static_cast<size_t>(f) * mod_ld + (threadIdx.x < 128 ? shift_off : scale_off) + i * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smod + threadIdx.x * 16)), "l"(src) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    const bool active = row < M;
+    const bf16* xr = x + static_cast<size_t>(active ? row : 0) * D;
     uint4 xu[CHUNKS], shu[CHUNKS], scu[CHUNKS];
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) xu[c] = *reinterpret_cast<const uint4*>(xr + c * 256 + lane * 8);
-    if (!AFFINE) {
-        int f = row / rows_per_frame;
+    if (!AFFINE && !staged) {
+        int f = (active ? row : 0) / rows_per_frame;
         if (frame_row != nullptr) f = frame_row[f];
         const bf16* mrow = mod + static_cast<size_t>(f) * mod_ld;
 #pragma unroll
@@ -43,6 +53,16 @@ ln_rows_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int M, const 
     float v[CHUNKS][8];
     float mean, rstd;
     ln_row_stats<CHUNKS>(xu, v, mean, rstd);
+    if (staged) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+            shu[c] = *reinterpret_cast<const uint4*>(smod + (c * 256 + lane * 8) * 2);
+            scu[c] = *reinterpret_cast<const uint4*>(smod + D * 2 + (c * 256 + lane * 8) * 2);
+        }
+    }
+    if (!active) return;
 
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {

@@ -126,7 +126,6 @@ def engine_steps():
     for label, env in (("default (weight-streaming GEMM, L2 prefetch, LN + temporal attention in the reduce)", {}),
                        ("separate LN / temporal-attention kernels", {"GTAV_FUSE": "0"}), ("no prefetch", {"GTAV_PREFETCH": "0"}),
                        ("to_out with 8 K-splits", {"GTAV_SK_SPLITS": "0,8,0,0"}), ("to_out with 16 K-splits", {"GTAV_SK_SPLITS": "0,16,0,0"}),
-                       ("to_qkv with 2 K-splits... n/a (smem); fc2 with 8 K-splits", {"GTAV_SK_SPLITS": "0,0,0,8"}),
                        ("tiled GEMM everywhere", {"GTAV_SKINNY": "0"}),
                        ("no PDL", {"GTAV_PDL_OFF_NOTE": "set GTAV_PDL=0 before start to test"})):
         if "GTAV_PDL_OFF_NOTE" in env:
