@@ -197,10 +197,6 @@ int build_shape(gtav_dit_plan_s* p, Shape* sh, int frames, bool allow_skinny) {
     // GTAV_SK_SPLITS="qkv,out,fc1,fc2": K-split override per GEMM kind (0 = the library's choice), for A/B measurements
     int so[4] = {0, 0, 0, 0};
     if (const char* e = getenv("GTAV_SK_SPLITS")) sscanf(e, "%d,%d,%d,%d", &so[0], &so[1], &so[2], &so[3]);
-    // to_out of one rollout (N = K = hidden): 4 splits instead of the 16 that would fill the SMs - the split-K exchange
-    // (S x 144 x N fp32 through L2, both ways) costs more than the idle SMs save; measured in the real step
-    // (scripts/bench_graph.py --engine): 16 splits 1.318 ms, 8 splits 1.306 ms, 4 splits 1.297 ms per last-frame step
-    if (so[1] == 0 && M == S) so[1] = 4;
     sh->fuse_ln = sh->sk[1] && sh->sk[3] && fuse_enabled();
     sh->fuse_tattn = sh->sk[0] && fuse_enabled() && (so[0] > 0 ? so[0] : skinny_pick_splits(M, 3 * D, D)) == 4 && p->T - 1 <= 7;
     const size_t cache_layer = static_cast<size_t>(p->B) * (p->T - 1) * S * 2 * D;

@@ -152,8 +152,10 @@ __device__ __forceinline__ uint2 skinny_epi4(float4 acc, const Epi4Ops& e) {
     o.y = pack_bf16x2(y[2], y[3]);
     return o;
 }
+// Not inlined: the reduce below calls it from up to 5 x 4 unrolled sites, and with the GELU epilogue inlined everywhere
+// the kernel grew to 50 KB of SASS - instruction fetch shows up in the ncu stall reasons of these ~9 us kernels.
 template <int EPI>
-__device__ __forceinline__ void skinny_store4(const GemmParams& g, int tok, int n, float4 acc, uint2 bias) {
+__device__ __noinline__ void skinny_store4(const GemmParams& g, int tok, int n, float4 acc, uint2 bias) {
     Epi4Ops e;
     if (EPI == EPI_BIAS_GATE_RES) e = skinny_epi4_load<EPI>(g, tok, n);
     e.bias = bias;
@@ -545,6 +547,10 @@ int skinny_pick_splits(int M, int N, int K) {
         if (rbs * s > sms) break;
         best = s;
     }
+    // Small weight matrices (to_out of one rollout: N = K = 1024): 4 splits instead of the 16 that would fill the SMs -
+    // the split-K exchange (S x 144 x N fp32 through L2, both ways) costs more than the idle SMs save.  Measured in the
+    // real step (scripts/bench_graph.py --engine): 16 splits 1.318 ms, 8 splits 1.306 ms, 4 splits 1.297 ms per step.
+    if (tiles == 1 && rbs <= 8 && kchunks <= 16 && best > 4) best = 4;
     return best;
 }
 
