@@ -11,7 +11,10 @@
 //     144-token frame tile (a legal UMMA N, no padding), accumulator D[128 x 144] fp32 in TMEM;
 //   * K is split over S CTAs per weight-row block so that (N/128)*S ~ the SM count; the W slab is ONE TMA box
 //     (3-D box spanning all its 64-wide K chunks: several small boxes per operand measured slower, bench_graph.py);
-//   * the W slab is requested before griddepcontrol.wait (weights do not depend on the previous kernel);
+//   * the W slab is requested before griddepcontrol.wait (weights do not depend on the previous kernel).  Measured
+//     alternatives for the operand loads, all slower in the real step (profiles/r01/bench_engine_v6.log): 2 / 4 boxes
+//     per operand from different warps (+1 % / +8 % step time: every extra TMA instruction costs), the token slab
+//     through cp.async with a software swizzle next to the TMA-loaded weights (+6 %);
 //   * partial accumulators go to an fp32 workspace (L2), the S CTAs of a row block meet on a
 //     counter, and each reduces + runs the fused epilogue for its 1/S share of the tokens, summing
 //     the partials in split order (deterministic);
