@@ -125,8 +125,6 @@ def engine_steps():
     out = torch.empty((1, 1, 16, 18, 32), dtype=torch.bfloat16, device=dev)
     for label, env in (("default (weight-streaming GEMM, L2 prefetch, LN + temporal attention in the reduce)", {}),
                        ("separate LN / temporal-attention kernels", {"GTAV_FUSE": "0"}), ("no prefetch", {"GTAV_PREFETCH": "0"}),
-                       ("token slab through TMA (not cp.async)", {"GTAV_SK_ALOAD": "0"}),
-                       ("2 TMA boxes per operand slab", {"GTAV_SK_BOXES": "2"}),
                        ("to_out with 16 K-splits", {"GTAV_SK_SPLITS": "0,16,0,0"}),
                        ("tiled GEMM everywhere", {"GTAV_SKINNY": "0"}),
                        ("no PDL", {"GTAV_PDL_OFF_NOTE": "set GTAV_PDL=0 before start to test"})):
