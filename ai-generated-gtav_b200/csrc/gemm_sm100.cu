@@ -5,12 +5,14 @@
 // with the surrounding elementwise ops (bias, GELU/SiLU, adaLN gate, residual) fused as epilogues that
 // round to bf16 exactly where the reference's autocast graph does.
 //
-// Structure (persistent CTAs over 128 x BN output tiles, double-buffered TMEM accumulator, 224 threads):
+// Structure (persistent CTAs over 128 x BN output tiles, double-buffered TMEM accumulator, 416 threads):
 //   warps 0,7: TMA producers of A - a stage is KC = 2 consecutive 64-wide K chunks of 128 rows, one box per thread
 //   warps 6,8: TMA producers of W - the same for BN weight rows; they run ahead of the previous kernel (PDL): weights
 //              do not depend on it
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1)
-//   warps 2-5: epilogue      - tcgen05.ld 32x32b from their TMEM lane quadrant, fused math, 16-byte stores
+//   warps 2-5, 9-12: epilogue - tcgen05.ld 32x32b from their TMEM lane quadrant (two warps per quadrant, half of the
+//              tile's columns each), fused math, 16-byte stores.  Eight warps: with four, a K = 1024 tile's GELU
+//              epilogue outlasts its mainloop (measured on the CTA-pair kernel: 668 -> 968 TFLOP/s on fc1)
 // smem full/empty mbarrier ring between the producers and the issuer; tcgen05.commit frees slots and signals
 // the epilogue.  Out-of-range rows / columns / K are zero-filled by TMA and masked in the epilogue.
 // Why four producer threads: measured on B200 (scripts/probe_tma*.cu, scripts/probe_mcast.cu, profiles/r01), one
@@ -29,7 +31,7 @@ namespace gtav {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;                 // one 128-byte-swizzled chunk
-static constexpr int GEMM_THREADS = 288;
+static constexpr int GEMM_THREADS = 416;      // 13 warps: 5 producer / MMA + 8 epilogue
 
 template <int BN, int STAGES, int KC>
 struct GemmSmem {
@@ -75,7 +77,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             for (int a = 0; a < 2; ++a) {
                 mbar_init(&tfull_bar[a], 1);
-                mbar_init(&tempty_bar[a], 4);         // one arrival per epilogue warp
+                mbar_init(&tempty_bar[a], blockDim.x > 288 ? 8 : 4);   // one arrival per epilogue warp
             }
             fence_barrier_init();
         }
@@ -152,9 +154,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         pdl_wait();
     } else {
         // idle until the first accumulator is ready: pull the NEXT GEMM's weights into L2 meanwhile
-        l2_prefetch_share(p.prefetch, p.prefetch_bytes, (blockIdx.x * 4 + (warp - 2)) * 32 + lane, gridDim.x * 128);
+        if (warp < 9) l2_prefetch_share(p.prefetch, p.prefetch_bytes, (blockIdx.x * 4 + (warp - 2)) * 32 + lane, gridDim.x * 128);
         pdl_wait();                               // bias / gate / residual may come from the previous kernel
         const int q = warp & 3;                   // TMEM lane quadrant this warp may read
+        const bool wide = blockDim.x > 288;       // 8 epilogue warps: two per quadrant, half of the columns each
+        const int c_lo = wide ? (warp >= 9 ? BN / 64 : 0) : 0, c_hi = wide ? (warp >= 9 ? BN / 32 : BN / 64) : BN / 32;
         int local = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
             const int m_blk = tile / n_tiles_n, n_blk = tile % n_tiles_n;
@@ -169,7 +173,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&tfull_bar[acc], (local >> 1) & 1);
             tcgen05_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = c_lo; c < c_hi; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
                 tmem_ld_wait();
@@ -295,13 +299,13 @@ int gemm_prepare(GemmOp* op, const bf16* A, int lda, const bf16* W, int ldw, con
     }
     const int m_tiles = (p.M + BM - 1) / BM;
     int bn = bn_override;
+    double best = 1e30;                     // cost of the best single-CTA tiling (cycles per K = 16 step x rounds)
     if (bn == 0) {
         // cost of one tile per K = 16 step, in cycles: the larger of the MMA (61 / 68 / 130 cycles at BN = 64 / 128 / 256,
         // scripts/probe_umma_rate.cu) and the operand ingest at the ~160 GB/s per SM two TMA producer warps reach
         // (71 / 95 / 142); times the number of rounds the persistent CTAs need.  Ties go to the wider tile.
         const int cand[3] = {256, 128, 64};
         const double cost[3] = {142.0, 95.0, 71.0};
-        double best = 1e30;
         for (int i = 0; i < 3; ++i) {
             if (cand[i] > 64 && p.N <= cand[i] / 2) continue;               // mostly padding
             const int tiles = m_tiles * ((p.N + cand[i] - 1) / cand[i]);
@@ -321,6 +325,21 @@ int gemm_prepare(GemmOp* op, const bf16* A, int lda, const bf16* W, int ldw, con
     // one 2-D box (rows x 64) per K chunk and producer thread, whatever the stage depth
     int rc = make_tmap(&op->tmA, A, p.M, p.K, lda, BM);
     if (rc) return rc;
+    // CTA pairs (gemm_sm100_2cta.cu) where the shape allows and the GEMM is large enough to be ingest-bound on one
+    // SM.  GTAV_GEMM_2CTA=0 / 1 forces the choice (1: whenever eligible).
+    op->two_cta = 0;
+    if (bn_override == 0 && gemm2_eligible(p.M, p.N, p.K)) {
+        const char* e = getenv("GTAV_GEMM_2CTA");
+        // same cost model for the CTA pair: a 256 x 256 tile pair on two SMs is MMA-bound (130 cycles per K = 16 step:
+        // each SM ingests a third less), rounds over the num_sms / 2 clusters.  E.g. (scripts/bench_2cta.py) M = 1152
+        // fc1: 80 pairs = 2 rounds x 130 vs 144 single tiles = 1 round x 142 -> single (22.5 vs 28.7 us measured);
+        // M = 5760 fc2: 92 pairs = 260 vs 184 tiles = 284 -> pair (57.3 vs 69.7 us measured).
+        const int pairs = ((p.M + 255) / 256) * (p.N / 256), clusters = num_sms() / 2;
+        // (several rounds only: its eight epilogue warps cost a single-round GEMM more than they save, see launch_one)
+        const bool big = pairs > clusters && static_cast<double>((pairs + clusters - 1) / clusters) * 130.0 < best;
+        op->two_cta = e != nullptr ? (e[0] == '1') : big;
+    }
+    if (op->two_cta && (rc = make_tmap(&op->tmB2, W, p.N, p.K, ldw, 128))) return rc;
     return make_tmap(&op->tmB, W, p.N, p.K, ldw, bn);
 }
 
@@ -335,7 +354,16 @@ static int launch_one(const GemmOp* op, cudaStream_t stream) {
     }
     const int tiles = ((op->p.N + BN - 1) / BN) * ((op->p.M + BM - 1) / BM);
     dim3 grid(tiles < num_sms() ? tiles : num_sms(), 1, 1);
-    GTAV_CUDA_OK(launch_k(kern, grid, dim3(GEMM_THREADS), L::TOTAL, stream, op->tmA, op->tmB, op->p));
+    // 8 epilogue warps (416 threads) when the CTAs run several tiles each (the epilogue of tile i must not outlast the
+    // mainloop of tile i + 1: fc1 at M = 9216 674 -> 993 TFLOP/s), 4 (288 threads) for single-round GEMMs, where the
+    // extra warps only cost (B = 8 last-frame step, M = 1152: 2.66 ms with 4, 2.82 ms with 8).  GTAV_EPI_WARPS=4|8 forces.
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("GTAV_EPI_WARPS");
+        forced = e == nullptr ? 0 : (e[0] == '4' ? 4 : 8);
+    }
+    const int epi_warps = forced ? forced : (tiles > num_sms() ? 8 : 4);
+    GTAV_CUDA_OK(launch_k(kern, grid, dim3(epi_warps == 8 ? GEMM_THREADS : 288), L::TOTAL, stream, op->tmA, op->tmB, op->p));
     return 0;
 }
 
@@ -356,6 +384,7 @@ static int launch_epi(const GemmOp* op, cudaStream_t stream) {
 }
 
 int gemm_run(const GemmOp* op, cudaStream_t stream) {
+    if (op->two_cta) return gemm2_run(op, stream);
     switch (op->epi) {
         case EPI_STORE: return launch_epi<EPI_STORE>(op, stream);
         case EPI_BIAS: return launch_epi<EPI_BIAS>(op, stream);

@@ -69,6 +69,8 @@ struct GemmParams {
 
 struct GemmOp {
     CUtensorMap tmA, tmB;
+    CUtensorMap tmB2;   // CTA-pair kernel (gemm_sm100_2cta.cu): boxes of 128 weight rows (each CTA loads half of a 256-wide tile)
+    int two_cta;        // 1: run the cta_group::2 kernel
     GemmParams p;
     int bn;      // tile width chosen at prepare time (64 / 128 / 256)
     int kc;      // 64-wide K chunks per TMA instruction / pipeline stage (1: 2-D maps, any K; 2: 3-D maps, K % 64 == 0)
@@ -80,6 +82,9 @@ struct GemmOp {
 int gemm_prepare(GemmOp* op, const bf16* A, int lda, const bf16* W, int ldw, const GemmParams& p, int epi,
                  int bn_override = 0);
 int gemm_run(const GemmOp* op, cudaStream_t stream);
+// CTA-pair variant (tcgen05.mma.cta_group::2, 256 x 256 tiles): M >= 256, N % 256 == 0, K % 128 == 0
+bool gemm2_eligible(int M, int N, int K);
+int gemm2_run(const GemmOp* op, cudaStream_t stream);
 
 // [rows, cols] bf16 row-major (leading dimension ld) viewed as [64 | rows | cols/64]: boxes of
 // box_rows x (box_chunks * 64) land in shared memory as box_chunks consecutive 128-byte-swizzled

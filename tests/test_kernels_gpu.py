@@ -359,3 +359,44 @@ def test_temporal_attention_last_frame_matches_dense(lib):
     err = float((out.float() - ref.float()).abs().max())
     assert err <= 2 ** -7 * float(ref.float().abs().max()), err
 
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (512, 512, 256), (1152, 1024, 1024), (1000, 3072, 1024), (2304, 1024, 4096),
+                                   (4608, 4096, 1024)])
+def test_gemm_cta_pair_equals_single_cta(lib, monkeypatch, M, N, K):
+    """tcgen05.mma.cta_group::2 on 256 x 256 tile pairs (gemm_sm100_2cta.cu) accumulates every output element over K in
+    the same order as the single-CTA kernel: same bits, including the ragged last row pair."""
+    Nmod = _N()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
+    W = (torch.randn((N, K), device="cuda", generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = (torch.randn((N,), device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("GTAV_GEMM_2CTA", mode)
+        outs[mode] = (run_gemm(lib, A, W, Nmod.EPI_STORE), run_gemm(lib, A, W, Nmod.EPI_BIAS_GELU_TANH, bias=bias))
+    close_bf16(outs["1"][0], A.float() @ W.float().t())
+    assert torch.equal(outs["0"][0], outs["1"][0]) and torch.equal(outs["0"][1], outs["1"][1])
+
+
+def test_gemm_cta_pair_gated_residual_in_place(lib, monkeypatch):
+    """The CTA-pair kernel with the adaLN gate + in-place residual epilogue and a frame_row indirection (B = 8 shape)."""
+    Nmod = _N()
+    monkeypatch.setenv("GTAV_GEMM_2CTA", "1")
+    M, N, K, S = 1152, 1024, 1024, 144
+    g = torch.Generator(device="cuda").manual_seed(77)
+    A = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
+    W = (torch.randn((N, K), device="cuda", generator=g) / 32).to(torch.bfloat16)
+    bias = (torch.randn((N,), device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    res = torch.randn((M, N), device="cuda", generator=g).to(torch.bfloat16)
+    gate = torch.randn((9, N), device="cuda", generator=g).to(torch.bfloat16)
+    frame_row = torch.tensor([3, 1, 4, 1, 5, 8, 2, 6], dtype=torch.int32, device="cuda")
+    y = r16(A.float() @ W.float().t() + bias.float())
+    grow = gate[frame_row.long()].float().repeat_interleave(S, dim=0)
+    ref = res.float() + r16(grow * y)
+    h = res.clone()
+    Nn = _N()
+    Nn.check(lib.gtav_gemm_bf16(A.data_ptr(), K, W.data_ptr(), K, h.data_ptr(), N, M, N, K, Nn.EPI_BIAS_GATE_RES, bias.data_ptr(),
+                                h.data_ptr(), N, gate.data_ptr(), N, frame_row.data_ptr(), S, 0, Nn.current_stream()), "gemm")
+    torch.cuda.synchronize()
+    close_bf16(h, ref, ulps=3.0, atol=4e-3, mag=res.float().abs() + (grow * y).abs())
