@@ -18,7 +18,7 @@ EXPORTS = [
     "gtav_attention_seq", "gtav_attention_temporal", "gtav_ddim_update", "gtav_dit_create", "gtav_dit_destroy",
     "gtav_dit_mod_width", "gtav_dit_workspace_bytes", "gtav_dit_plan_create", "gtav_dit_plan_destroy",
     "gtav_dit_conditioning", "gtav_dit_backbone", "gtav_dit_forward", "gtav_vae_create", "gtav_vae_destroy",
-    "gtav_vae_workspace_bytes", "gtav_vae_plan_create", "gtav_vae_plan_destroy", "gtav_vae_encode", "gtav_vae_decode",
+    "gtav_vae_workspace_bytes", "gtav_vae_plan_create", "gtav_vae_plan_destroy", "gtav_vae_encode", "gtav_vae_encode_moments", "gtav_vae_decode",
     "gtav_sampler_cond_rows", "gtav_sampler_scratch_bytes", "gtav_sampler_create", "gtav_sampler_destroy",
     "gtav_sampler_run_frame", "gtav_noise_clamp",
 ]
@@ -101,6 +101,7 @@ def load() -> C.CDLL:
         "gtav_vae_plan_create": [vp, i, vp, sz, C.POINTER(vp)],
         "gtav_vae_plan_destroy": [vp],
         "gtav_vae_encode": [vp, vp, i, fp, C.c_float, i, vp],
+        "gtav_vae_encode_moments": [vp, vp, i, fp, fp, vp],
         "gtav_vae_decode": [vp, fp, C.c_float, vp, i, vp],
         "gtav_sampler_cond_rows": [i, i, i],
         "gtav_sampler_create": [vp, i, i, i, i, fp, vp, fp, ip, vp, sz, i, vp, C.POINTER(vp)],

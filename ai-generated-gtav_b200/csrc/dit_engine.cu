@@ -209,14 +209,18 @@ int build_shape(gtav_dit_plan_s* p, Shape* sh, int frames, bool allow_skinny) {
         GemmParams p1 = gp(p->mlp, 4 * D, hw.fc1_b, M, 4 * D, D);
         GemmParams p2 = gp(p->h, D, hw.fc2_b, M, D, 4 * D);
         p2.res = p->h; p2.ldr = D; p2.gate = modl + 5 * D; p2.gate_ld = W; p2.rows_per_frame = S;
-        // each GEMM pulls the next one's weights into L2 while it runs (weights: 2 bytes per element)
+        // each tiled GEMM pulls the next one's weights into L2 while it runs (weights: 2 bytes per element).  Not the
+        // weight-streaming kernel: it requests its own weight slab first thing, before the dependency wait, and the
+        // extra L2 fills then only compete with the operand loads (bench_graph.py --engine: 1.208 ms per step with the
+        // prefetch, 1.191 ms without; tiled passes: 2.312 with, 2.331 without).  GTAV_PREFETCH=0 / 1 forces off / on.
         const size_t DD = static_cast<size_t>(D) * D * 2;
         const char* pfenv = getenv("GTAV_PREFETCH");
-        if (!(pfenv != nullptr && pfenv[0] == '0')) {
-            pq.prefetch = hw.out_w; pq.prefetch_bytes = DD;
-            po.prefetch = hw.fc1_w; po.prefetch_bytes = 4 * DD;
-            p1.prefetch = hw.fc2_w; p1.prefetch_bytes = 4 * DD;
-            if (i + 1 < nh) { p2.prefetch = h->halves[i + 1].qkv_w; p2.prefetch_bytes = 3 * DD; }
+        const bool pf_off = pfenv != nullptr && pfenv[0] == '0', pf_force = pfenv != nullptr && pfenv[0] == '1';
+        if (!pf_off) {
+            if (pf_force || !sh->sk[0]) { pq.prefetch = hw.out_w; pq.prefetch_bytes = DD; }
+            if (pf_force || !sh->sk[1]) { po.prefetch = hw.fc1_w; po.prefetch_bytes = 4 * DD; }
+            if (pf_force || !sh->sk[2]) { p1.prefetch = hw.fc2_w; p1.prefetch_bytes = 4 * DD; }
+            if ((pf_force || !sh->sk[3]) && i + 1 < nh) { p2.prefetch = h->halves[i + 1].qkv_w; p2.prefetch_bytes = 3 * DD; }
         }
         // fused reduces: LN2 of this half after to_out, LN1 of the next half (or the final layer's norm) after fc2,
         // temporal attention after the temporal half's to_qkv

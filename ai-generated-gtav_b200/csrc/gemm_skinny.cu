@@ -366,13 +366,32 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     const int total = tiles * SK_NT;
     const uint32_t tmem_cols = total <= 256 ? 256u : 512u;
 
+    // Both operand loads go out BEFORE the CTA-wide set-up barrier: thread 0 initialises the W barrier and requests the
+    // W slab at once (weights do not depend on the previous kernel), warp 1 initialises the token-slab barriers, waits for
+    // the previous kernel (griddepcontrol.wait) and requests the slab - neither needs the TMEM allocation that the
+    // barrier below publishes, and the MMA thread first touches these barriers after it.
     if (gemm_cta && warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmW);
-        tma_prefetch_desc(&tmA);
         mbar_init(bar_w, 1);
-        for (int t = 0; t < 3; ++t) mbar_init(&bar_a[t], 1);
         mbar_init(bar_acc, 1);
         fence_barrier_init();
+        mbar_arrive_expect_tx(bar_w, chunks * SK_W_CHUNK);
+        tma_load_3d(sW, &tmW, bar_w, 0, rb * 128, kc0);
+        SK_STAMP(1);                                                           // W requested
+    }
+    if (gemm_cta && warp == 1) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmA);
+            for (int t = 0; t < 3; ++t) mbar_init(&bar_a[t], 1);
+            fence_barrier_init();
+        }
+        pdl_wait();
+        if (lane == 0) {
+            for (int t = 0; t < tiles; ++t) {
+                mbar_arrive_expect_tx(&bar_a[t], chunks * SK_A_CHUNK);
+                tma_load_3d(sA + t * chunks * SK_A_CHUNK, &tmA, &bar_a[t], 0, t * SK_NT, kc0);
+            }
+        }
     }
     if (gemm_cta && warp == 2) {
         tmem_alloc(tmem_slot, tmem_cols);
@@ -384,12 +403,6 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     const uint32_t tmem_base = gemm_cta ? *tmem_slot : 0u;
     pdl_trigger();
     if (!gemm_cta && threadIdx.x == 128) SK_STAMP(1);                          // set-up done
-
-    if (gemm_cta && warp == 0 && lane == 0) {
-        mbar_arrive_expect_tx(bar_w, chunks * SK_W_CHUNK);
-        tma_load_3d(sW, &tmW, bar_w, 0, rb * 128, kc0);
-        SK_STAMP(1);                                                           // set-up done, W requested
-    }
     if (warp >= 4)     // idle until the accumulator is ready: pull the NEXT GEMM's weights into L2 meanwhile
         l2_prefetch_share(p.g.prefetch, p.g.prefetch_bytes, (blockIdx.x * 4 + (warp - 4)) * 32 + lane, gridDim.x * 128);
     if (gemm_cta && warp == 2) {
@@ -414,12 +427,6 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         pdl_wait();
     } else {
         pdl_wait();
-        if (gemm_cta && warp == 1 && lane == 0) {
-            for (int t = 0; t < tiles; ++t) {
-                mbar_arrive_expect_tx(&bar_a[t], chunks * SK_A_CHUNK);
-                tma_load_3d(sA + t * chunks * SK_A_CHUNK, &tmA, &bar_a[t], 0, t * SK_NT, kc0);
-            }
-        }
     }
     // ---- past griddepcontrol.wait: the previous kernels' results are visible.  Start the loads the reduce will need.
     // Rendezvous group: the S CTAs of this row block (group rb of `counters`, 4 ints each), or, in the fused modes, ALL

@@ -156,9 +156,28 @@ int gtav_vae_plan_create(gtav_vae_t h, int n_frames, void* workspace, size_t wor
 
 void gtav_vae_plan_destroy(gtav_vae_plan_t p) { delete p; }
 
+static int vae_encode_moments(gtav_vae_plan_t p, const void* img, int img_is_bf16, gtav_stream_t stream);
+
 int gtav_vae_encode(gtav_vae_plan_t p, const void* img, int img_is_bf16, float* mean_out, float scale, int round_bf16,
                     gtav_stream_t stream) {
     if (!p || !img || !mean_out) { set_error("vae_encode: null argument"); return -1; }
+    int rc = vae_encode_moments(p, img, img_is_bf16, stream);
+    if (rc) return rc;
+    return launch_take_mean(p->mom, 64, mean_out, p->M, p->eng->cfg.latent_dim, scale, round_bf16, stream);
+}
+
+int gtav_vae_encode_moments(gtav_vae_plan_t p, const void* img, int img_is_bf16, float* mean_out, float* logvar_out,
+                            gtav_stream_t stream) {
+    if (!p || !img || !mean_out || !logvar_out) { set_error("vae_encode_moments: null argument"); return -1; }
+    int rc = vae_encode_moments(p, img, img_is_bf16, stream);
+    if (rc) return rc;
+    const int C = p->eng->cfg.latent_dim;
+    if ((rc = launch_take_mean(p->mom, 64, mean_out, p->M, C, 1.0f, 0, stream))) return rc;
+    return launch_take_mean(p->mom + C, 64, logvar_out, p->M, C, 1.0f, 0, stream);     // columns C .. 2C-1 of quant_conv
+}
+
+// patchify -> patch embed -> encoder blocks -> enc_norm -> quant_conv: the 2*latent moments of every token in p->mom
+static int vae_encode_moments(gtav_vae_plan_t p, const void* img, int img_is_bf16, gtav_stream_t stream) {
     const gtav_vae_s* e = p->eng;
     const gtav_vae_config& c = e->cfg;
     int rc = launch_patchify(img, img_is_bf16, p->pa, e->patch_ld, p->N, 3, c.seq_h * c.patch, c.seq_w * c.patch, c.patch, 0, 0L, stream);
@@ -167,8 +186,7 @@ int gtav_vae_encode(gtav_vae_plan_t p, const void* img, int img_is_bf16, float* 
     for (size_t i = 0; i < e->enc.size(); ++i)
         if ((rc = run_block(p, e->enc[i], p->enc[i], stream))) return rc;
     if ((rc = launch_ln_affine(p->h, p->hn, p->M, c.dim, e->w.enc_norm_w, e->w.enc_norm_b, stream))) return rc;
-    if ((rc = gemm_run(&p->g_quant, stream))) return rc;
-    return launch_take_mean(p->mom, 64, mean_out, p->M, c.latent_dim, scale, round_bf16, stream);
+    return gemm_run(&p->g_quant, stream);
 }
 
 int gtav_vae_decode(gtav_vae_plan_t p, const float* z, float divisor, void* out, int to_u8, gtav_stream_t stream) {

@@ -28,19 +28,27 @@ def _linear(i, o):
 
 
 class DiagonalGaussianDistribution:
-    """`mean` is what generate.py:56 consumes; `logvar` clamped like model/vae.py:29."""
+    """The posterior of reference model/vae.py:19-45 for dim=2 moments [N, seq, 2*latent] (already split): `mean` is what
+    generate.py:56 consumes; `logvar` is clamped to [-30, 20], `std` / `var` derived from it, `sample()` draws
+    mean + std * randn, `mode()` is the mean; `deterministic` zeroes std / var."""
 
-    def __init__(self, mean: torch.Tensor, logvar: torch.Tensor | None = None):
+    def __init__(self, mean: torch.Tensor, logvar: torch.Tensor | None = None, deterministic: bool = False):
         self.mean = mean
-        self.logvar = None if logvar is None else torch.clamp(logvar, -30.0, 20.0)
+        self.deterministic = deterministic or logvar is None
+        self.logvar = torch.zeros_like(mean) if logvar is None else torch.clamp(logvar, -30.0, 20.0)
+        if self.deterministic:
+            self.std = self.var = torch.zeros_like(mean)
+        else:
+            self.std = torch.exp(0.5 * self.logvar)
+            self.var = torch.exp(self.logvar)
+        self.parameters = torch.cat([self.mean, self.logvar], dim=-1)
+        self.dims = [1, 2]
 
     def mode(self):
         return self.mean
 
     def sample(self):
-        if self.logvar is None:
-            return self.mean
-        return self.mean + torch.exp(0.5 * self.logvar) * torch.randn_like(self.mean)
+        return self.mean + self.std * torch.randn(self.mean.shape, device=self.mean.device, dtype=self.mean.dtype)
 
 
 class AutoencoderKL(nn.Module):
@@ -211,8 +219,24 @@ class AutoencoderKL(nn.Module):
                                              float(scale), int(round_bf16), N.current_stream()), "gtav_vae_encode")
         return out
 
+    @torch.no_grad()
     def encode(self, x):
-        return DiagonalGaussianDistribution(self.encode_mean(x).to(torch.bfloat16))
+        """`vae.encode(x)` (model/vae.py:306-322): the full posterior, both halves of quant_conv's bf16 output."""
+        N.require_cuda(x, "x")
+        if x.shape[1:] != (3, self.input_height, self.input_width):
+            raise AssertionError(f"Input image size {tuple(x.shape[1:])} doesn't match model "
+                                 f"(3, {self.input_height}, {self.input_width}).")
+        self._pack()
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        x = x.contiguous()
+        n = x.shape[0]
+        mean = torch.empty((n, self.seq_len, self.latent_dim), dtype=torch.float32, device=x.device)
+        logvar = torch.empty_like(mean)
+        with torch.cuda.device(x.device):
+            N.check(N.load().gtav_vae_encode_moments(self._plan(n), x.data_ptr(), int(x.dtype == torch.bfloat16), mean.data_ptr(),
+                                                     logvar.data_ptr(), N.current_stream()), "gtav_vae_encode_moments")
+        return DiagonalGaussianDistribution(mean.to(torch.bfloat16), logvar.to(torch.bfloat16))
 
     @torch.no_grad()
     def decode(self, z, divisor: float = 1.0, to_uint8: bool = False):

@@ -195,6 +195,10 @@ void gtav_vae_plan_destroy(gtav_vae_plan_t p);
  * re-rounded to bf16 when round_bf16 (generate.py:56 multiplies a bf16 tensor). */
 int gtav_vae_encode(gtav_vae_plan_t p, const void* img, int img_is_bf16, float* mean_out, float scale, int round_bf16,
                     gtav_stream_t stream);
+/* Both halves of the posterior (DiagonalGaussianDistribution, model/vae.py:19-45: torch.chunk(moments, 2)): mean_out and
+ * logvar_out fp32 [N, seq, latent] holding the bf16 values of quant_conv's output, unclamped. */
+int gtav_vae_encode_moments(gtav_vae_plan_t p, const void* img, int img_is_bf16, float* mean_out, float* logvar_out,
+                            gtav_stream_t stream);
 /* z fp32 [N, seq, latent], divided by `divisor` first (generate.py:241) -> out: bf16 [N,3,H,W] (to_u8 = 0)
  * or uint8 [N,H,W,3] with the pixel epilogue of generate.py:241-244 fused (to_u8 = 1). */
 int gtav_vae_decode(gtav_vae_plan_t p, const float* z, float divisor, void* out, int to_u8, gtav_stream_t stream);

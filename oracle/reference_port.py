@@ -297,6 +297,12 @@ def _vae_block(rd, sd, cfg, pre, x, ang):
 def vae_encode_mean(sd, cfg: VAEConfig, img, rd: Rounding = FP32):
     """`vae.encode(img).mean`: img [N,3,H,W] in [-1,1] -> [N, seq_len, latent_dim]
     (model/vae.py:306-322; the posterior's logvar/std are unused by generate.py:56)."""
+    return vae_encode_moments(sd, cfg, img, rd)[..., : cfg.latent_dim]
+
+
+def vae_encode_moments(sd, cfg: VAEConfig, img, rd: Rounding = FP32):
+    """quant_conv's output [N, seq_len, 2*latent_dim] = (mean | logvar) of DiagonalGaussianDistribution
+    (model/vae.py:19-45, 306-322), logvar unclamped."""
     N = img.shape[0]
     p = cfg.patch_size
     patches = img.reshape(N, 3, cfg.seq_h, p, cfg.seq_w, p).permute(0, 2, 4, 1, 3, 5)
@@ -306,8 +312,7 @@ def vae_encode_mean(sd, cfg: VAEConfig, img, rd: Rounding = FP32):
     for n in range(cfg.enc_depth):
         x = _vae_block(rd, sd, cfg, f"encoder.{n}", x, ang)
     x = _layer_norm(x, sd["enc_norm.weight"], sd["enc_norm.bias"])
-    moments = _linear(rd, x, sd["quant_conv.weight"], sd["quant_conv.bias"])
-    return moments[..., : cfg.latent_dim]
+    return _linear(rd, x, sd["quant_conv.weight"], sd["quant_conv.bias"])
 
 
 def vae_decode(sd, cfg: VAEConfig, z, rd: Rounding = FP32):

@@ -124,7 +124,7 @@ def engine_steps():
     rows = torch.arange(5, dtype=torch.int32, device=dev)
     out = torch.empty((1, 1, 16, 18, 32), dtype=torch.bfloat16, device=dev)
     for label, env in (("default (weight-streaming GEMM, L2 prefetch, LN + temporal attention in the reduce)", {}),
-                       ("separate LN / temporal-attention kernels", {"GTAV_FUSE": "0"}), ("no prefetch", {"GTAV_PREFETCH": "0"}),
+                       ("separate LN / temporal-attention kernels", {"GTAV_FUSE": "0"}), ("L2 prefetch of the next weights also in the weight-streaming GEMM", {"GTAV_PREFETCH": "1"}),
                        ("to_out with 16 K-splits", {"GTAV_SK_SPLITS": "0,16,0,0"}),
                        ("tiled GEMM everywhere", {"GTAV_SKINNY": "0"}),
                        ("no PDL", {"GTAV_PDL_OFF_NOTE": "set GTAV_PDL=0 before start to test"})):

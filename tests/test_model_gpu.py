@@ -221,3 +221,26 @@ def test_vae_decode_uint8_matches_pixel_epilogue():
     u8 = vae.decode(z, divisor=0.07843137255, to_uint8=True)
     ref = torch.clamp(((dec + 1) / 2) * 255, 0, 255).byte().permute(0, 2, 3, 1)
     assert u8.shape == (2, 360, 640, 3) and torch.equal(u8, ref)
+
+
+def test_vae_posterior_moments():
+    """`vae.encode(x)` returns the whole DiagonalGaussianDistribution of the reference (model/vae.py:19-45): mean AND
+    logvar (clamped), std / var, sample(), mode(); both halves against the CPU oracle's quant_conv output."""
+    sd, vae = vae_pair(1, 1)
+    cfg = VAEConfig(enc_depth=1, dec_depth=1)
+    img = seeded_rand((2, 3, 360, 640), 97) * 2 - 1
+    post = vae.encode(img.cuda())
+    mom = rp.vae_encode_moments(sd, cfg, img, rp.BF16)
+    check(post.mean, mom[..., :16], (6e-2, 6e-3), "posterior mean vs bf16 oracle")
+    check(post.logvar, torch.clamp(mom[..., 16:], -30.0, 20.0), (6e-2, 6e-3), "posterior logvar vs bf16 oracle")
+    assert torch.equal(post.mean, vae.encode_mean(img.cuda()).to(torch.bfloat16))       # same kernels as the mean-only path
+    assert torch.equal(post.mode(), post.mean) and post.parameters.shape == (2, 576, 32)
+    assert torch.allclose(post.std.float(), torch.exp(0.5 * post.logvar.float()), rtol=1e-2)
+    assert torch.allclose(post.var.float(), torch.exp(post.logvar.float()), rtol=2e-2)
+    torch.manual_seed(0)
+    s1 = post.sample()
+    assert s1.shape == post.mean.shape and not torch.equal(s1, post.mean)
+    z = (s1.float() - post.mean.float()) / post.std.float()
+    assert abs(float(z.mean())) < 0.05 and abs(float(z.std()) - 1.0) < 0.05          # mean + std * N(0, 1)
+    rec, post2, zz = vae.autoencode(img.cuda(), sample_posterior=False)
+    assert rec.shape == (2, 3, 360, 640) and torch.equal(zz, post2.mean)
