@@ -490,7 +490,12 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         // release: partial stores ordered before the arrival below (fence + CTA barrier + relaxed atomic); the
         // acq_rel fence is lighter than __threadfence()'s sequentially-consistent one
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        tcgen05_fence_before();
         __syncthreads();
+        if (warp == 2) {                           // the accumulator has been read by everyone: give the TMEM back now,
+            tcgen05_fence_after();                 // off the kernel's exit path
+            tmem_dealloc(tmem_base, tmem_cols);
+        }
         if (threadIdx.x == 128) {
             SK_STAMP(5);                                                       // partials written + fenced
             skinny_rendezvous(meet, meet_n, sense0);
@@ -525,9 +530,11 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         }
         if (threadIdx.x == 128) SK_STAMP(7);
     }
-    tcgen05_fence_before();
-    __syncthreads();
-    if (gemm_cta && warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+    if (S == 1 && gemm_cta) {                      // no split: the epilogue warps read the accumulator until here
+        tcgen05_fence_before();
+        __syncthreads();
+        if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host
