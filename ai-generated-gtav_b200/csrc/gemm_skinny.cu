@@ -80,10 +80,7 @@ __device__ __forceinline__ void skinny_rendezvous(int* grp, int n, int which) {
     uint32_t spins = 0;
     while (ld_acquire_gpu(cnt) < n) {
         __nanosleep(32);
-        if (++spins > (1u << 24)) {
-            printf("gtav: split-K rendezvous timed out (block %d)\n", blockIdx.x);
-            __trap();
-        }
+        if (++spins > (1u << 24)) __trap();    // a protocol bug fails the launch instead of hanging the GPU
     }
     *reinterpret_cast<volatile int*>(grp + ((which & 1) ^ 1)) = 0;
     *reinterpret_cast<volatile int*>(grp + 2) = (which & 1) ^ 1;
@@ -213,6 +210,36 @@ __device__ __forceinline__ void skinny_reduce(const GemmParams& g, const float* 
     }
 }
 
+// Sum of the S partials at p0, p0 + stride, ... in split order, all loads in flight together.
+template <int S>
+__device__ __forceinline__ float4 skinny_sum4(const float* p0, size_t stride) {
+    float4 v[S];
+#pragma unroll
+    for (int s2 = 0; s2 < S; ++s2) v[s2] = __ldcg(reinterpret_cast<const float4*>(p0 + s2 * stride));
+    float4 acc = v[0];
+#pragma unroll
+    for (int s2 = 1; s2 < S; ++s2) { acc.x += v[s2].x; acc.y += v[s2].y; acc.z += v[s2].z; acc.w += v[s2].w; }
+    return acc;
+}
+// Any split count: one token per warp at a time, partials summed in split order, up to 16 loads in flight.
+template <int EPI>
+__device__ __forceinline__ void skinny_reduce_any(const GemmParams& g, const float* part, int S, int total, int lo, int hi, int wid,
+                                                  int lane, int n0, uint2 bias) {
+    const float* base = part + 4 * lane;
+    const size_t stride = static_cast<size_t>(total) * 128;
+#pragma unroll 1
+    for (int tok = lo + wid; tok < hi; tok += 8) {
+        const float* p0 = base + static_cast<size_t>(tok) * 128;
+        float4 acc;
+        switch (S) {
+            case 2: acc = skinny_sum4<2>(p0, stride); break;
+            case 8: acc = skinny_sum4<8>(p0, stride); break;
+            default: acc = skinny_sum4<16>(p0, stride); break;
+        }
+        skinny_store4<EPI>(g, tok, n0 + 4 * lane, acc, bias);
+    }
+}
+
 // ---- fused reduces: the CTAs meet on ALL row-block counters and every CTA then owns whole token rows (token
 // blockIdx.x, blockIdx.x + gridDim.x, ...), so that row-wise work that follows the Linear can run right here instead
 // of in another kernel of the latency-bound last-frame chain.  Their operands other than the partial sums (epilogue
@@ -238,17 +265,6 @@ __device__ __forceinline__ Epi4Ops skinny_ln_preload(const SkinnyParams& p, int 
     e.res = *reinterpret_cast<const uint2*>(g.res + static_cast<size_t>(tok) * g.ldr + n);
     *reinterpret_cast<uint4*>(smod + threadIdx.x * 16) = m;
     return e;
-}
-// Sum of the S partials at p0, p0 + stride, ... in split order, all loads in flight together.
-template <int S>
-__device__ __forceinline__ float4 skinny_sum4(const float* p0, size_t stride) {
-    float4 v[S];
-#pragma unroll
-    for (int s2 = 0; s2 < S; ++s2) v[s2] = __ldcg(reinterpret_cast<const float4*>(p0 + s2 * stride));
-    float4 acc = v[0];
-#pragma unroll
-    for (int s2 = 1; s2 < S; ++s2) { acc.x += v[s2].x; acc.y += v[s2].y; acc.z += v[s2].z; acc.w += v[s2].w; }
-    return acc;
 }
 __device__ __forceinline__ void skinny_reduce_ln(const SkinnyParams& p, int S, int total, int warp, int lane, uint8_t* smod,
                                                  uint8_t* srow, Epi4Ops e) {
@@ -410,10 +426,12 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             constexpr uint32_t idesc = umma_idesc_bf16(128, SK_NT);
             mbar_wait(bar_w, 0);
             SK_STAMP(2);                                                       // W slab landed
+#pragma unroll 1
             for (int t = 0; t < tiles; ++t) {
                 mbar_wait(&bar_a[t], 0);
                 if (t == 0) SK_STAMP(3);                                       // first A tile landed
                 tcgen05_fence_after();
+#pragma unroll 1
                 for (int ch = 0; ch < chunks; ++ch) {
                     const uint64_t dw = umma_desc_sw128(smem_u32(sW + ch * SK_W_CHUNK));
                     const uint64_t da = umma_desc_sw128(smem_u32(sA + (t * chunks + ch) * SK_A_CHUNK));
@@ -510,13 +528,11 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         const GemmParams& g = p.g;
         const int lo = split * total / S, hi = (split + 1) * total / S;
         const float* part = p.ws + static_cast<size_t>(rb) * S * total * 128;
-        switch (S) {
-            case 2: skinny_reduce<EPI, 2>(g, part, total, lo, hi, warp, lane, rb * 128, epre.bias); break;
-            case 4: skinny_reduce<EPI, 4>(g, part, total, lo, hi, warp, lane, rb * 128, epre.bias); break;
-            case 8: skinny_reduce<EPI, 8>(g, part, total, lo, hi, warp, lane, rb * 128, epre.bias); break;
-            case 16: skinny_reduce<EPI, 16>(g, part, total, lo, hi, warp, lane, rb * 128, epre.bias); break;
-            default: __trap();
-        }
+        // S = 4 (to_qkv, to_out, fc1 of one rollout: the hot launches) gets the fully unrolled reduce with every load of
+        // a warp's tokens in flight at once; the other split counts share one run-time loop - four unrolled variants
+        // made these latency-bound kernels ~50 % larger, and instruction fetch is a measured cost for them.
+        if (S == 4) skinny_reduce<EPI, 4>(g, part, total, lo, hi, warp, lane, rb * 128, epre.bias);
+        else skinny_reduce_any<EPI>(g, part, S, total, lo, hi, warp, lane, rb * 128, epre.bias);
         if (threadIdx.x == 128) SK_STAMP(7);                                   // reduced + stored (this warp)
     }
     if (FUSE != SK_FUSE_NONE) {
