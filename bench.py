@@ -10,8 +10,10 @@ kernels).  One JSON line is printed by rank 0:
   value  : generated frames/s with the prompt already resident in HBM (device-timed, max over ranks)
   e2e    : same metric through the public API with HOST buffers: pinned prompt video H2D and uint8 frames
            D2H inside the timed region
-  roofline: tensor roofline of the dominant kernel (the tcgen05 GEMM): algorithmic GEMM FLOPs of a DiT step
-           / the GEMM time of a step measured with CUDA events (weights HBM-cold, as in the real step)
+  roofline: the dominant kernel of the default (frame-cache) algorithm at B = 1, the weight-streaming tcgen05 GEMM,
+           against the measured HBM bandwidth: algorithmic bytes of its 128 launches per step / their CUDA-event time
+           (weights HBM-cold, as in the real step); at B > 1 and in the `dense` leg the tiled / CTA-pair GEMM against
+           the measured sustained bf16 tensor throughput
   cpu_baseline: the CPU port of the reference (oracle/) timed on this box's host cores on a bounded sample
 With --impl reference only the CPU arm runs (the Python reference cannot travel to the GPU box; the
 oracle port is its restatement) and prints the same line with "impl": "reference".
