@@ -23,13 +23,46 @@ attn_seq_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads,
     attn_seq_body<SEQ, KB, WARPS, ROT_PAIRS, false>(qkv, out, heads, rot, sK, sV, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, 0);
 }
 
+// DiT spatial attention (144 tokens, rotary on all 32 pairs): the rotary table [144][32] (cos, sin) is a CONSTANT of the
+// model, so every CTA copies it into shared memory with cp.async BEFORE griddepcontrol.wait - as global loads issued when
+// the K / V rows arrive, it was a second dependent L2 round trip in a ~5 us kernel of the latency-bound last-frame chain.
+static constexpr int ROT144_BYTES = 144 * 32 * 8;
+static constexpr int ATTN144_SMEM = 2 * 144 * SROW * 2 + ROT144_BYTES;
+__global__ void __launch_bounds__(3 * 32)
+attn_seq144_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, const float2* __restrict__ rot) {
+    extern __shared__ __align__(16) uint8_t smem144[];
+    bf16* sK = reinterpret_cast<bf16*>(smem144);
+    bf16* sV = sK + 144 * SROW;
+    float2* sRot = reinterpret_cast<float2*>(smem144 + 2 * 144 * SROW * 2);
+    for (int i = threadIdx.x; i < ROT144_BYTES / 16; i += 3 * 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(reinterpret_cast<uint8_t*>(sRot) + i * 16)),
+                     "l"(reinterpret_cast<const uint8_t*>(rot) + i * 16) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    pdl_trigger();
+    pdl_wait();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    attn_seq_body<144, 144, 3, 32, false>(qkv, out, heads, sRot, sK, sV, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, 0);
+}
+
 int launch_attention_seq(const bf16* qkv, bf16* out, int groups, int seq, int heads, const float2* rot, int rot_pairs,
                          cudaStream_t s) {
     if (groups <= 0) return 0;
     if (seq == 144 && rot_pairs == 32) {
         // all 144 keys of a head staged in one pass (every global load of the block in flight at once); the queries
         // are split over 3 CTAs of 3 warps so that 48 SMs share the loads at B = 1
-        GTAV_CUDA_OK(launch_k(attn_seq_kernel<144, 144, 3, 32>, dim3(3, heads, groups), dim3(3 * 32), 0, s, qkv, out, heads, rot));
+        if (groups * heads * 3 <= 2 * 148) {
+            // few frames (last-frame steps of up to 6 rollouts, context passes): latency matters, every CTA has an SM
+            // (almost) to itself - the variant with the rotary table staged in its 78 KB of shared memory
+            static bool configured = false;
+            if (!configured) {
+                GTAV_CUDA_OK(cudaFuncSetAttribute(attn_seq144_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN144_SMEM));
+                configured = true;
+            }
+            GTAV_CUDA_OK(launch_k(attn_seq144_kernel, dim3(3, heads, groups), dim3(3 * 32), ATTN144_SMEM, s, qkv, out, heads, rot));
+        } else {
+            GTAV_CUDA_OK(launch_k(attn_seq_kernel<144, 144, 3, 32>, dim3(3, heads, groups), dim3(3 * 32), 0, s, qkv, out, heads, rot));
+        }
     } else if (seq == 576 && rot_pairs == 16) {
         GTAV_CUDA_OK(launch_k(attn_seq_kernel<576, 64, 4, 16>, dim3(9, heads, groups), dim3(4 * 32), 0, s, qkv, out, heads, rot));
     } else {
