@@ -51,7 +51,9 @@ enum gtav_epilogue {
 
 /* out[M,N] = epilogue(A[M,K] @ W[N,K]^T) on the tcgen05 GEMM.  lda/ldw/ldo/ldr/gate_ld in elements
  * (multiples of 8).  gate row of output row r is gate + frame_row[r / rows_per_frame] * gate_ld
- * (frame_row NULL = identity).  bn = 0 lets the library pick the tile width (64/128/256). */
+ * (frame_row NULL = identity).  bn = 0 lets the library pick the tile width (64/128/256) and, for multi-round
+ * shapes with N % 256 == 0 and K % 128 == 0, the CTA-pair kernel (tcgen05.mma.cta_group::2, 256x256 tile pairs);
+ * both produce the same bits. */
 int gtav_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
                    int epilogue, const void* bias, const void* res, int ldr, const void* gate, int gate_ld,
                    const int* frame_row, int rows_per_frame, int bn, gtav_stream_t stream);
