@@ -79,7 +79,7 @@ __device__ __forceinline__ void skinny_rendezvous(int* grp, int n, int which) {
     asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(cnt) : "memory");
     uint32_t spins = 0;
     while (ld_acquire_gpu(cnt) < n) {
-        __nanosleep(32);
+        // (no back-off: one polling thread per CTA, the wake-up latency is on the critical path of every launch)
         if (++spins > (1u << 24)) __trap();    // a protocol bug fails the launch instead of hanging the GPU
     }
     *reinterpret_cast<volatile int*>(grp + ((which & 1) ^ 1)) = 0;
