@@ -195,18 +195,8 @@ __device__ __forceinline__ void skinny_reduce(const GemmParams& g, const float* 
                 }
             }
         }
-        return;
-    }
-#pragma unroll 1
-    for (int tok = lo + wid; tok < hi; tok += 8) {
-        float4 v[S];
-#pragma unroll
-        for (int s2 = 0; s2 < S; ++s2)
-            v[s2] = __ldcg(reinterpret_cast<const float4*>(base + (static_cast<size_t>(s2) * total + tok) * 128));
-        float4 acc = v[0];
-#pragma unroll
-        for (int s2 = 1; s2 < S; ++s2) { acc.x += v[s2].x; acc.y += v[s2].y; acc.z += v[s2].z; acc.w += v[s2].w; }
-        skinny_store4<EPI>(g, tok, n0 + 4 * lane, acc, bias);
+    } else {
+        static_assert(S <= 4, "the unrolled reduce is instantiated for S = 4 only; other split counts use skinny_reduce_any");
     }
 }
 
