@@ -44,6 +44,16 @@ def build_ref_vae(ref, cfg: VAEConfig, sd):
     return m.eval()
 
 
+def mint_trainer_schedule(ref):
+    """DiffusionTrainer.register_buffers (reference train_dit.py:288-327): the same schedule with clamp_min 1e-6, the integer
+    DDIM level table of 16 steps and the stabilization level it yields."""
+    betas = ref.sigmoid_beta_schedule(1000, clamp_min=0.000001)
+    abar = torch.cumprod(1.0 - betas.to(torch.float32), dim=0)
+    levels = torch.linspace(0, 999, 17).long()
+    save_file({"betas_f64": betas.contiguous(), "alphas_cumprod_f32": abar.contiguous(), "noise_range_16": levels.contiguous()},
+              os.path.join(OUT, "schedule_trainer.safetensors"))
+
+
 @torch.inference_mode()
 def main():
     warnings.filterwarnings("ignore")
@@ -56,6 +66,8 @@ def main():
     abar = torch.cumprod(1.0 - betas.float(), dim=0)
     save_file({"betas_f64": betas.contiguous(), "alphas_cumprod_f32": abar.contiguous()},
               os.path.join(OUT, "schedule.safetensors"))
+
+    mint_trainer_schedule(ref)
 
     # ---- DiT.forward -----------------------------------------------------------------------
     out = {}

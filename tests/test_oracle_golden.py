@@ -116,3 +116,20 @@ def test_bf16_rounding_model_is_close_to_fp32():
     v16 = rp.dit_forward(dit_state(2), cfg, x, t, a, rp.BF16)
     err = (v32 - v16).abs()
     assert 0 < float(err.max()) < 6e-2 and float(err.mean()) < 1.2e-2
+
+
+def test_trainer_schedule_known_answers(golden):
+    """DiffusionTrainer.register_buffers of the reference (train_dit.py:288-327): clamp_min 1e-6 schedule, integer level
+    table, stabilization level - the oracle port, the product's utils and the product's inference-side trainer (its
+    buffers are built on the host, so this runs without a GPU) against the golden minted from the unmodified reference."""
+    g = golden("schedule_trainer")
+    betas = rp.sigmoid_beta_schedule(1000, clamp_min=0.000001)
+    assert torch.equal(betas, g["betas_f64"])
+    from gtav_b200.utils import sigmoid_beta_schedule
+    assert torch.equal(sigmoid_beta_schedule(1000, clamp_min=0.000001), g["betas_f64"])
+    from gtav_b200.train_dit import DiffusionTrainer, TrainingConfig
+    tr = DiffusionTrainer(TrainingConfig(), dit=None, vae=None, device=torch.device("cpu"))
+    assert torch.equal(tr.alphas_cumprod.reshape(-1), g["alphas_cumprod_f32"])
+    assert torch.equal(tr.alphas_cumprod_inference.reshape(-1), g["alphas_cumprod_f32"])
+    assert torch.equal(tr.noise_range, g["noise_range_16"]) and torch.equal(tr.noise_range_inference, g["noise_range_16"])
+    assert int(tr.stabilization_level) == int(g["noise_range_16"][1]) == 62
