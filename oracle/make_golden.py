@@ -55,6 +55,20 @@ def mint_trainer_schedule(ref):
 
 
 @torch.inference_mode()
+def mint_vae_posterior(ref):
+    """The whole DiagonalGaussianDistribution of `vae.encode(img)` (reference model/vae.py:19-45, 306-322) for the small
+    VAE case: raw moments (mean | logvar), clamped logvar and std."""
+    c = CASES_VAE["e1_d1"]
+    cfg = VAEConfig(enc_depth=c["enc_depth"], dec_depth=c["dec_depth"])
+    vae = build_ref_vae(ref, cfg, make_vae_state(cfg, seed=0))
+    img = seeded_rand((c["N"], 3, 360, 640), c["seed"]) * 2 - 1
+    post = vae.encode(img)
+    save_file({"moments": post.parameters.float().contiguous(), "logvar": post.logvar.float().contiguous(),
+               "std": post.std.float().contiguous(), "mode": post.mode().float().contiguous()},
+              os.path.join(OUT, "vae_posterior.safetensors"))
+
+
+@torch.inference_mode()
 def main():
     warnings.filterwarnings("ignore")
     torch.set_num_threads(os.cpu_count())
@@ -118,6 +132,7 @@ def main():
         out[f"{name}.dec_abs_sum"] = dec.double().abs().sum().reshape(1)
         print(name, "mean std", float(mean.std()), "dec std", float(dec.std()))
     save_file(out, os.path.join(OUT, "vae.safetensors"))
+    mint_vae_posterior(ref)
 
     # ---- a short autoregressive rollout driven exactly like reference generate.py:186-244 ----
     c = ROLLOUT

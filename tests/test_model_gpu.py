@@ -223,11 +223,17 @@ def test_vae_decode_uint8_matches_pixel_epilogue():
     assert u8.shape == (2, 360, 640, 3) and torch.equal(u8, ref)
 
 
-def test_vae_posterior_moments():
+def test_vae_posterior_moments(golden):
     """`vae.encode(x)` returns the whole DiagonalGaussianDistribution of the reference (model/vae.py:19-45): mean AND
-    logvar (clamped), std / var, sample(), mode(); both halves against the CPU oracle's quant_conv output."""
+    logvar (clamped), std / var, sample(), mode(); both halves against the CPU oracle's quant_conv output and against the
+    golden minted from the unmodified reference (fp32)."""
     sd, vae = vae_pair(1, 1)
     cfg = VAEConfig(enc_depth=1, dec_depth=1)
+    c = CASES_VAE["e1_d1"]
+    gp = golden("vae_posterior")
+    pg = vae.encode((seeded_rand((c["N"], 3, 360, 640), c["seed"]) * 2 - 1).cuda())
+    check(pg.mean, gp["moments"][..., :16], (1.5e-1, 2e-2), "posterior mean vs reference fp32")
+    check(pg.logvar, gp["logvar"], (1.5e-1, 2e-2), "posterior logvar vs reference fp32")
     img = seeded_rand((2, 3, 360, 640), 97) * 2 - 1
     post = vae.encode(img.cuda())
     mom = rp.vae_encode_moments(sd, cfg, img, rp.BF16)

@@ -133,3 +133,19 @@ def test_trainer_schedule_known_answers(golden):
     assert torch.equal(tr.alphas_cumprod_inference.reshape(-1), g["alphas_cumprod_f32"])
     assert torch.equal(tr.noise_range, g["noise_range_16"]) and torch.equal(tr.noise_range_inference, g["noise_range_16"])
     assert int(tr.stabilization_level) == int(g["noise_range_16"][1]) == 62
+
+
+def test_vae_posterior_matches_reference(golden):
+    """Both halves of quant_conv's output (mean | logvar), the clamp and std of DiagonalGaussianDistribution
+    (reference model/vae.py:19-45) - the oracle's vae_encode_moments against the unmodified reference."""
+    c = CASES_VAE["e1_d1"]
+    cfg = VAEConfig(enc_depth=c["enc_depth"], dec_depth=c["dec_depth"])
+    g = golden("vae_posterior")
+    img = seeded_rand((c["N"], 3, 360, 640), c["seed"]) * 2 - 1
+    mom = rp.vae_encode_moments(vae_state(c["enc_depth"], c["dec_depth"]), cfg, img)
+    assert mom.shape == (c["N"], 576, 32)
+    assert float((mom - g["moments"]).abs().max()) < 5e-4
+    logvar = torch.clamp(mom[..., 16:], -30.0, 20.0)
+    assert float((logvar - g["logvar"]).abs().max()) < 5e-4
+    assert float((torch.exp(0.5 * logvar) - g["std"]).abs().max()) < 5e-4 * float(g["std"].max())
+    assert torch.equal(g["mode"], g["moments"][..., :16])
