@@ -91,7 +91,7 @@ def load() -> C.CDLL:
         "gtav_dit_create": [C.POINTER(DitConfig), C.POINTER(DitWeights), C.POINTER(vp)],
         "gtav_dit_destroy": [vp],
         "gtav_dit_mod_width": [vp],
-        "gtav_dit_plan_create": [vp, i, i, i, vp, sz, C.POINTER(vp)],
+        "gtav_dit_plan_create": [vp, i, i, i, vp, sz, vp, C.POINTER(vp)],
         "gtav_dit_plan_destroy": [vp],
         "gtav_dit_conditioning": [vp, i64p, fp, vp],
         "gtav_dit_backbone": [vp, vp, i, ip, vp, vp],
@@ -144,3 +144,14 @@ def current_stream() -> int:
 def require_cuda(t, name: str):
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor: gtav_b200 runs only on sm_100a GPUs (no CPU fallback)")
+
+
+def param_signature(module):
+    """(data_ptr, version) of every parameter: a change of either means the packed bf16 copies are stale.
+    Inference tensors (modules built or moved under torch.inference_mode, as the reference's generate.py does for
+    load_models / main) have no version counter: they get version -1 and in-place edits of them are only seen through
+    load_state_dict / .to() (which mark the module dirty) or an explicit repack()."""
+    sig = []
+    for p in module.parameters():
+        sig.append((p.data_ptr(), -1 if p.is_inference() else p._version))
+    return tuple(sig)

@@ -46,13 +46,6 @@ struct gtav_dit_plan_s {
     bf16* kv_cache;          // [depth][B*(T-1)*tokens][2*hidden]: rotated K and V of the context frames per temporal layer
     float* sk_ws;            // split-K partial sums of the weight-streaming GEMM / of the persistent step kernel
     int* sk_counters;
-    // persistent last-frame step kernel (B == 1): per-half descriptors (device), counters, LayerNorm partials
-    MegaHalfDev* mega_halves;
-    unsigned* mega_sync;
-    uint8_t* mega_buf[6];    // hn_t, att_t, mlp_t, qkv_h, ws_out, ws_fc2
-    int* zero_row;
-    MegaParams mega;         // launch parameters of the step kernel (last_row / trace filled per launch)
-    bool use_mega;
     GemmOp g_t0, g_t2, g_ada;
     Shape full, ctx, last;   // all T frames / the T-1 context frames / the last frame only
 };
@@ -92,12 +85,6 @@ void carve(gtav_dit_plan_s* p, void* ws, size_t* total) {
     size_t ws_bytes = p->B <= 3 ? skinny_workspace_bytes(m_last) : 0;
     p->sk_ws = reinterpret_cast<float*>(c.take(ws_bytes / sizeof(bf16)));
     p->sk_counters = reinterpret_cast<int*>(c.take(1024));      // 512 ints: 4 per rendezvous group (gemm_skinny.cu)
-    if (p->B == 1) {
-        p->mega_halves = reinterpret_cast<MegaHalfDev*>(c.take(static_cast<size_t>(2 * e->cfg.depth) * sizeof(MegaHalfDev) / sizeof(bf16)));
-        p->mega_sync = reinterpret_cast<unsigned*>(c.take(mega_sync_bytes() / sizeof(bf16)));
-        for (int i = 0; i < 6; ++i) p->mega_buf[i] = reinterpret_cast<uint8_t*>(c.take(mega_buffer_bytes(i) / sizeof(bf16)));
-        p->zero_row = reinterpret_cast<int*>(c.take(64));
-    }
     *total = c.off;
 }
 
@@ -113,60 +100,10 @@ bool skinny_enabled() {
     return !(e != nullptr && e[0] == '0');
 }
 
-// The persistent step kernel is opt-in (GTAV_MEGA=1): parity-green, but measured slower than the PDL-chained kernels
-// (profiles/r01/step_kernel_trace_v2.txt: ~69 us vs ~46 us per half-block; its L2-mediated split-K exchange and grid
-// barriers cost what the kernel boundaries did).
 // GTAV_FUSE=0 keeps LayerNorm and temporal attention as kernels of their own (same results, bit for bit).
 bool fuse_enabled() {
     const char* e = getenv("GTAV_FUSE");
     return !(e != nullptr && e[0] == '0');
-}
-
-bool mega_enabled() {
-    const char* e = getenv("GTAV_MEGA");
-    return e != nullptr && e[0] == '1';
-}
-
-// Device-side descriptors of the persistent last-frame step kernel (B == 1): one weight tensor map per GEMM.
-int build_mega(gtav_dit_plan_s* p) {
-    const gtav_dit_s* h = p->eng;
-    const int nh = 2 * h->cfg.depth, D = h->cfg.hidden;
-    std::vector<MegaHalfDev> host(nh);
-    for (int i = 0; i < nh; ++i) {
-        const gtav_dit_half& hw = h->halves[i];
-        const void* w[4] = {hw.qkv_w, hw.out_w, hw.fc1_w, hw.fc2_w};
-        for (int k = 0; k < 4; ++k) {
-            const int rc = mega_make_weight_map(&host[i].tm[k], static_cast<const bf16*>(w[k]), k);
-            if (rc) return rc;
-        }
-        host[i].out_b = static_cast<const bf16*>(hw.out_b);
-        host[i].fc1_b = static_cast<const bf16*>(hw.fc1_b);
-        host[i].fc2_b = static_cast<const bf16*>(hw.fc2_b);
-        host[i].mod_off = i * 6 * D;
-        host[i].pad_ = 0;
-    }
-    if (cudaMemcpy(p->mega_halves, host.data(), host.size() * sizeof(MegaHalfDev), cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemset(p->mega_sync, 0, mega_sync_bytes()) != cudaSuccess || cudaMemset(p->zero_row, 0, 64) != cudaSuccess) {
-        set_error("dit_plan_create: uploading the step-kernel descriptors failed: %s", cudaGetErrorString(cudaGetLastError()));
-        return -2;
-    }
-    MegaParams& mp = p->mega;
-    mp = MegaParams{};
-    mp.halves = p->mega_halves; mp.n_halves = nh;
-    mp.h = p->h;
-    mp.hn_t = p->mega_buf[0]; mp.att_t = p->mega_buf[1]; mp.mlp_t = p->mega_buf[2];
-    mp.qkv_h = reinterpret_cast<bf16*>(p->mega_buf[3]);
-    mp.ws_out = reinterpret_cast<float*>(p->mega_buf[4]); mp.ws_fc2 = reinterpret_cast<float*>(p->mega_buf[5]);
-    mp.mod = p->mod; mp.mod_ld = h->mod_width;
-    mp.sync = p->mega_sync;
-    mp.kv_cache = p->kv_cache;
-    mp.cache_layer_stride = static_cast<size_t>(p->B) * (p->T - 1) * h->tokens * 2 * D;
-    mp.ctx_frames = p->T - 1;
-    mp.rot_s = reinterpret_cast<const float2*>(h->w.rot_spatial);
-    mp.rot_t = reinterpret_cast<const float2*>(h->w.rot_temporal);
-    mp.grid = mega_grid();
-    p->use_mega = true;
-    return 0;
 }
 
 // Descriptors of the backbone GEMMs for `frames` frames per rollout.  allow_skinny: use the weight-streaming
@@ -268,14 +205,6 @@ int run_backbone(gtav_dit_plan_s* p, const Shape* sh, int mode, const void* x, i
     const float2* rot_s = reinterpret_cast<const float2*>(e->w.rot_spatial);
     const float2* rot_t = reinterpret_cast<const float2*>(e->w.rot_temporal);
     const size_t cache_layer = static_cast<size_t>(p->B) * (p->T - 1) * S * 2 * D;
-    const bool mega = mode == MODE_LAST && p->use_mega;
-    if (mega) {
-        // all 2*depth half-blocks in one persistent kernel (dit_step_mega.cu)
-        MegaParams mp = p->mega;
-        mp.last_row = frame_row != nullptr ? frame_row : p->zero_row;
-        if (const char* tr = getenv("GTAV_MEGA_TRACE")) mp.trace = reinterpret_cast<long long*>(strtoull(tr, nullptr, 0));
-        if ((rc = mega_run(mp, stream))) return rc;
-    }
     bool hn_ready = false;                  // the previous fc2's reduce already wrote this half's LN1 output
     // GTAV_ENGINE_TRACE=<device address>: phase time stamps of every weight-streaming GEMM of this pass, [launch][160][8]
     // int64 globaltimer ns (scripts/trace_step.py); profiling aid, unset in production
@@ -288,7 +217,7 @@ int run_backbone(gtav_dit_plan_s* p, const Shape* sh, int mode, const void* x, i
         if (trace_base != nullptr) o.trace = trace_base + static_cast<size_t>(trace_k++) * 160 * 8;
         return skinny_run(&o, stream);
     };
-    for (int i = 0; i < 2 * c.depth && !mega; ++i) {
+    for (int i = 0; i < 2 * c.depth; ++i) {
         const int off = i * 6 * D;          // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
         if (!hn_ready && (rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, off, off + D, frame_row, S, stream))) return rc;
         if (sh->sk[0]) rc = run_skinny(sh->s_qkv[i]);
@@ -328,7 +257,7 @@ int run_backbone(gtav_dit_plan_s* p, const Shape* sh, int mode, const void* x, i
     }
     if (out == nullptr) return 0;
     const int foff = 2 * c.depth * 6 * D;   // final layer: shift, scale
-    if (!(hn_ready && !mega) && (rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, foff, foff + D, frame_row, S, stream))) return rc;
+    if (!hn_ready && (rc = launch_ln_modulate(p->h, p->hn, M, D, p->mod, W, foff, foff + D, frame_row, S, stream))) return rc;
     if ((rc = gemm_run(&sh->g_final, stream))) return rc;
     return launch_dit_unpatchify(p->yfin, static_cast<bf16*>(out), F, c.in_channels, c.grid_h, c.grid_w, c.patch, stream);
 }
@@ -338,7 +267,7 @@ int run_backbone(gtav_dit_plan_s* p, const Shape* sh, int mode, const void* x, i
 extern "C" {
 
 const char* gtav_last_error(void) { return get_error(); }
-int gtav_abi_version(void) { return 2; }
+int gtav_abi_version(void) { return 3; }
 
 int gtav_dit_create(const gtav_dit_config* cfg, const gtav_dit_weights* w, gtav_dit_t* out) {
     if (!cfg || !w || !out) { set_error("dit_create: null argument"); return -1; }
@@ -380,7 +309,7 @@ size_t gtav_dit_workspace_bytes(gtav_dit_t h, int B, int T, int cond_rows) {
 }
 
 int gtav_dit_plan_create(gtav_dit_t h, int B, int T, int cond_rows, void* workspace, size_t workspace_bytes,
-                         gtav_dit_plan_t* out) {
+                         gtav_stream_t stream, gtav_dit_plan_t* out) {
     if (!h || !workspace || !out) { set_error("dit_plan_create: null argument"); return -1; }
     if (B <= 0 || T <= 0 || T > h->cfg.max_frames || cond_rows <= 0) {
         set_error("dit_plan_create: B=%d T=%d cond_rows=%d out of range (T <= max_frames=%d)", B, T, cond_rows, h->cfg.max_frames);
@@ -412,8 +341,9 @@ int gtav_dit_plan_create(gtav_dit_t h, int B, int T, int cond_rows, void* worksp
     if (rc == 0) rc = build_shape(p, &p->full, T, false);
     if (rc == 0 && T >= 2) rc = build_shape(p, &p->ctx, T - 1, false);
     if (rc == 0) rc = build_shape(p, &p->last, 1, true);
-    if (rc == 0 && cudaMemset(p->sk_counters, 0, 2048) != cudaSuccess) { set_error("dit_plan_create: clearing the split-K counters failed"); rc = -2; }
-    if (rc == 0 && B == 1 && mega_enabled()) rc = build_mega(p);
+    // on the caller's stream: the workspace may be a recycled block of a stream-ordered allocator (torch's), and the
+    // plan's kernels run on that stream too - a memset on the legacy stream would order with neither
+    if (rc == 0 && cudaMemsetAsync(p->sk_counters, 0, 2048, stream) != cudaSuccess) { set_error("dit_plan_create: clearing the split-K counters failed"); rc = -2; }
     if (rc) { delete p; return rc < 0 ? rc : -1; }
     *out = p;
     return 0;

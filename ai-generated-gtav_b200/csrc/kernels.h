@@ -128,38 +128,6 @@ int skinny_prepare(SkinnyOp* op, const bf16* A, int lda, const bf16* W, int ldw,
                    int* counters, int splits_override = 0, const SkinnyFuseParams* fuse = nullptr);
 int skinny_run(const SkinnyOp* op, cudaStream_t stream);
 
-// ---------------------------------------------------------------- persistent last-frame step (dit_step_mega.cu)
-// The 2*depth half-blocks of a last-frame DiT step at B = 1 (144 rows) as one persistent kernel: see the file header.
-struct alignas(64) MegaHalfDev {
-    CUtensorMap tm[4];                  // weight maps: to_qkv, to_out, fc1, fc2 (3-D view, boxes of 32 / 16 rows x 16 chunks)
-    const bf16 *out_b, *fc1_b, *fc2_b;
-    int mod_off;                        // column of this half's (shift, scale, gate) x 2 inside a modulation row
-    int pad_;
-};
-struct MegaParams {
-    const MegaHalfDev* halves;          // device array [n_halves]
-    int n_halves;
-    bf16* h;                            // [144, D] row-major residual stream (in: patch-embed output, out: after the last block)
-    uint8_t *hn_t, *att_t, *mlp_t;      // pre-tiled GEMM operands [K/64][144][64] bf16, 128-byte swizzled (K = D, D, 4D)
-    bf16* qkv_h;                        // [3][heads][144][72]: rotated q, rotated k, v per head, rows padded to 72
-    float *ws_out, *ws_fc2;             // fp32 results of to_out [64][144][16] and fc2 partials [128][144][32]
-    const bf16* mod;                    // conditioning table, row = *last_row
-    int mod_ld;
-    const int* last_row;
-    unsigned* sync;                     // zero-initialised counters, mega_sync_bytes()
-    const bf16* kv_cache;               // [layer][ctx_frames*144][2D]
-    size_t cache_layer_stride;          // elements between temporal layers
-    int ctx_frames;
-    const float2 *rot_s, *rot_t;
-    int grid;
-    long long* trace;                   // optional [grid][2][32] globaltimer stamps (profiling aid), normally null
-};
-size_t mega_sync_bytes();
-size_t mega_buffer_bytes(int which);    // 0 hn_t, 1 att_t, 2 mlp_t, 3 qkv_h, 4 ws_out, 5 ws_fc2
-int mega_grid();
-int mega_make_weight_map(CUtensorMap* out, const bf16* W, int kind);
-int mega_run(const MegaParams& p, cudaStream_t stream);
-
 // ---------------------------------------------------------------- row kernels (norm_mod.cu)
 // out = bf16( LN(x) * bf16(1 + bf16(scale + 1e-6)) + shift ), LN without affine, eps 1e-6.
 // shift/scale of row r live at mod + frame_row[r / rows_per_frame] * mod_ld + {shift_off, scale_off}.

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import weakref
 
 import torch
 from torch import nn
@@ -90,6 +91,10 @@ class DiT(nn.Module):
         self._engine = None      # (handle, keep-alive tensors)
         self._packed_sig = None
         self._plans = {}
+        self._dirty = False
+        self._pack_generation = 0
+        self._dependants = weakref.WeakSet()     # Samplers holding handles / CUDA graphs built on this module's plans
+        self.register_load_state_dict_post_hook(lambda module, _keys: module._mark_dirty())
 
     # ------------------------------------------------------------------ init (same distributions as dit.py:304-326)
     @torch.no_grad()
@@ -115,10 +120,26 @@ class DiT(nn.Module):
 
     # ------------------------------------------------------------------ weight packing
     def _signature(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return N.param_signature(self)
+
+    def _mark_dirty(self, *_):
+        self._dirty = True
+
+    def _apply(self, fn, *a, **k):          # .to() / .cuda() / .half(): new storage -> repack on the next call
+        self._dirty = True
+        return super()._apply(fn, *a, **k)
+
+    def repack(self):
+        """Force a re-pack of the bf16 weights on the next call (after editing parameters in place in a way the version
+        counters cannot show, e.g. on inference tensors)."""
+        self._dirty = True
 
     def _release(self):
         lib = N.load()
+        # sampler handles and their captured graphs point into the plans' workspaces and at the packed weights: they
+        # go first (the Sampler rebuilds them on its next call)
+        for dep in list(self._dependants):
+            dep._invalidate()
         for plan, _ws in self._plans.values():
             lib.gtav_dit_plan_destroy(plan)
         self._plans = {}
@@ -138,9 +159,11 @@ class DiT(nn.Module):
         adaLN linears are concatenated into one [depth*2*6D + 2D, D] matrix so that all modulation
         vectors come out of a single GEMM."""
         sig = self._signature()
-        if self._engine is not None and sig == self._packed_sig:
+        if self._engine is not None and sig == self._packed_sig and not self._dirty:
             return
         self._release()
+        self._dirty = False
+        self._pack_generation += 1
         lib = N.load()
         dev = self.final_layer.linear.weight.device
         if dev.type != "cuda":
@@ -215,7 +238,10 @@ class DiT(nn.Module):
             ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
             base = (ws.data_ptr() + 1023) & ~1023
             plan = N.vp()
-            N.check(lib.gtav_dit_plan_create(handle, B, T, cond_rows, base, nbytes, C.byref(plan)), "gtav_dit_plan_create")
+            with torch.cuda.device(dev):
+                # the caller's current stream: the one the workspace was just allocated on and the passes will run on
+                N.check(lib.gtav_dit_plan_create(handle, B, T, cond_rows, base, nbytes, N.current_stream(), C.byref(plan)),
+                        "gtav_dit_plan_create")
             self._plans[key] = (plan, ws)
         return self._plans[key][0]
 

@@ -91,6 +91,9 @@ class AutoencoderKL(nn.Module):
         self._engine = None
         self._packed_sig = None
         self._plans = {}
+        self._dirty = False
+        self._pack_generation = 0
+        self.register_load_state_dict_post_hook(lambda module, _keys: module._mark_dirty())
 
     @torch.no_grad()
     def initialize_weights(self):
@@ -108,7 +111,19 @@ class AutoencoderKL(nn.Module):
 
     # ------------------------------------------------------------------ packing
     def _signature(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return N.param_signature(self)
+
+    def _mark_dirty(self, *_):
+        self._dirty = True
+
+    def _apply(self, fn, *a, **k):          # .to() / .cuda() / .half(): new storage -> repack on the next call
+        self._dirty = True
+        return super()._apply(fn, *a, **k)
+
+    def repack(self):
+        """Force a re-pack of the bf16 weights on the next call (after editing parameters in place in a way the version
+        counters cannot show, e.g. on inference tensors)."""
+        self._dirty = True
 
     def _release(self):
         lib = N.load()
@@ -128,9 +143,11 @@ class AutoencoderKL(nn.Module):
     @torch.no_grad()
     def _pack(self):
         sig = self._signature()
-        if self._engine is not None and sig == self._packed_sig:
+        if self._engine is not None and sig == self._packed_sig and not self._dirty:
             return
         self._release()
+        self._dirty = False
+        self._pack_generation += 1
         lib = N.load()
         dev = self.predictor.weight.device
         if dev.type != "cuda":

@@ -37,7 +37,7 @@ SCALING_FACTOR = 0.07843137255   # generate.py:51,241
 
 class Sampler:
     def __init__(self, dit, vae=None, noise_steps: int = 100, stabilization_level: int = 15, noise_abs_max: float = 20.0,
-                 max_noise_level: int = 1000, use_graph: bool = True, frame_cache: bool = True):
+                 max_noise_level: int = 1000, use_graph: bool = True, frame_cache: bool = True, alphas_cumprod=None):
         self.dit, self.vae = dit, vae
         self.steps = int(noise_steps)
         self.stab = int(stabilization_level)
@@ -45,19 +45,27 @@ class Sampler:
         self.use_graph = bool(use_graph)
         self.frame_cache = bool(frame_cache)
         self.levels = [int(v) for v in torch.linspace(0, max_noise_level - 1, self.steps + 1).tolist()]
-        betas = sigmoid_beta_schedule(max_noise_level).float()
-        self.abar_host = torch.cumprod(1.0 - betas, dim=0)
+        if alphas_cumprod is None:              # generate.py:195-197 (clamp_min 1e-4, the schedule's default)
+            betas = sigmoid_beta_schedule(max_noise_level).float()
+            self.abar_host = torch.cumprod(1.0 - betas, dim=0)
+        else:                                   # a caller's own table, e.g. the trainer's clamp_min 1e-6 one (train_dit.py:297-307)
+            self.abar_host = alphas_cumprod.detach().reshape(-1).to(device="cpu", dtype=torch.float32).clone()
+            if self.abar_host.numel() != max_noise_level:
+                raise RuntimeError(f"alphas_cumprod must hold {max_noise_level} levels, got {self.abar_host.numel()}")
         self._ctx = {}          # (B, T) -> dict(sampler handle, buffers)
         self._stream = None
+        dit._dependants.add(self)   # the DiT drops our handles / graphs before it releases the plans they were built on
         self.frame_elems = dit.in_channels * dit.input_h * dit.input_w
 
     # ------------------------------------------------------------------ per-(B,T) context
     def _context(self, B, T, dev):
         key = (B, T)
+        # first: a load_state_dict / in-place weight change / .to() since the last call re-packs the weights, which
+        # releases every plan and (through DiT._release -> _invalidate) every cached context of this sampler
+        self.dit._pack()
         if key in self._ctx:
             return self._ctx[key]
         lib = N.load()
-        self.dit._pack()
         rows = lib.gtav_sampler_cond_rows(B, T, self.steps)
         plan = self.dit._plan(B, T, rows)
         n = self.frame_elems
@@ -81,6 +89,13 @@ class Sampler:
         for ctx in self._ctx.values():
             lib.gtav_sampler_destroy(ctx["h"])
         self._ctx = {}
+
+    def _invalidate(self):
+        """Called by the DiT before it releases its plans (weights re-packed): captured graphs and sampler handles refer
+        to the old plans' workspaces and weight copies, so they are destroyed once pending work has drained."""
+        if self._ctx:
+            torch.cuda.synchronize()
+            self.close()
 
     def __del__(self):
         try:
@@ -149,6 +164,12 @@ class Sampler:
                 T = i + 1 - start
                 if noise is not None:
                     chunk = noise[:, i - n_prompt].to(device=dev, dtype=torch.float32).reshape(B, n).contiguous()
+                elif isinstance(generator, (list, tuple)):
+                    # one generator per rollout (shard.rollout_generators: seeded by the GLOBAL rollout id, so a
+                    # rollout's noise does not depend on which rank owns it or on how many rollouts share the batch)
+                    if len(generator) != B:
+                        raise RuntimeError(f"sample_latents: {len(generator)} generators for {B} rollouts")
+                    chunk = torch.stack([torch.randn((n,), device=dev, generator=g) for g in generator])
                 else:
                     chunk = torch.randn((B, n), device=dev, generator=generator)
                 act_win = None if actions is None else actions[:, start:start + T]

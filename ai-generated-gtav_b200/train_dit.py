@@ -131,7 +131,8 @@ class DiffusionTrainer:
     def _sampler(self) -> Sampler:
         key = (self.config.ddim_noise_steps_inference, int(self.stabilization_level), float(self.config.noise_abs_max))
         if key not in self._samplers:
-            self._samplers[key] = Sampler(self.dit, self.vae, noise_steps=key[0], stabilization_level=key[1], noise_abs_max=key[2])
+            self._samplers[key] = Sampler(self.dit, self.vae, noise_steps=key[0], stabilization_level=key[1], noise_abs_max=key[2],
+                                          max_noise_level=self.max_noise_level, alphas_cumprod=self.alphas_cumprod_inference)
         return self._samplers[key]
 
     @torch.inference_mode()
@@ -158,11 +159,14 @@ class DiffusionTrainer:
         return actions
 
     @torch.inference_mode()
-    def predict(self, test_loader, epoch=0, global_step=0, num_frames=32, generator=None, video_path=None, stepwise=False):
+    def predict(self, test_loader, epoch=0, global_step=0, num_frames=32, generator=None, video_path=None, stepwise=False,
+                noise=None):
         """Generate `num_frames` frames from the first n_prompt_frames of the loader's first batch (train_dit.py:373-469).
         Returns (pixels uint8 [1, num_frames, H, W, 3], latents); writes an mp4 only when video_path is given (the
         reference always writes debug_visualizations/test_*.mp4).  stepwise=True runs the reference's literal
-        per-step loop through denoise_step instead of the graph-captured Sampler (same results)."""
+        per-step loop through denoise_step instead of the graph-captured Sampler (same results).  noise: optional
+        [1, num_frames - n_prompt, C, h, w] N(0,1) draws used instead of torch.randn (the reference draws them from the
+        global RNG, train_dit.py:419-421)."""
         self.dit.eval()
         prompt = next(iter(test_loader))
         frames = prompt["video"][:1, : self.config.n_prompt_frames].to(self.device)
@@ -170,12 +174,15 @@ class DiffusionTrainer:
         smp = self._sampler()
         x = self.encode_frames(frames, dtype=self.dtype)
         if not stepwise:
-            x = smp.sample_latents(x, actions, num_frames, generator=generator)
+            x = smp.sample_latents(x, actions, num_frames, generator=generator, noise=noise)
         else:
             n_prompt = x.shape[1]
             x = x.float()
             for i in range(n_prompt, num_frames):
-                new_frame = torch.randn((x.shape[0], 1, *x.shape[2:]), device=self.device, generator=generator)
+                if noise is not None:
+                    new_frame = noise[:, i - n_prompt: i - n_prompt + 1].to(device=self.device, dtype=torch.float32)
+                else:
+                    new_frame = torch.randn((x.shape[0], 1, *x.shape[2:]), device=self.device, generator=generator)
                 new_frame = torch.clamp(new_frame, -self.config.noise_abs_max, self.config.noise_abs_max)
                 x = torch.cat([x, new_frame], dim=1)
                 start_frame = max(0, i + 1 - self.dit.max_frames)
@@ -194,7 +201,7 @@ class DiffusionTrainer:
         return pixels, x
 
     @torch.inference_mode()
-    def predict_noise(self, test_loader, epoch=0, global_step=0, generator=None):
+    def predict_noise(self, test_loader, epoch=0, global_step=0, generator=None, noise=None):
         """Noise the context frames of a clip to stabilization_level - 1, replace the last frame by clamped noise and
         denoise it (train_dit.py:471-552, without the matplotlib panel).  Returns (x_noisy after denoising, clean
         latents, v_pred of the final step)."""
@@ -206,12 +213,16 @@ class DiffusionTrainer:
         latents = self.encode_frames(frames).float()
         B = latents.shape[0]
         x_noisy = latents.clone()
-        ctx_noise = torch.randn(x_noisy[:, :-1].shape, device=self.device, generator=generator)
+        if noise is not None:
+            noise = noise.to(device=self.device, dtype=torch.float32)
+            ctx_noise = noise[:, :-1]
+        else:
+            ctx_noise = torch.randn(x_noisy[:, :-1].shape, device=self.device, generator=generator)
         ctx_noise = torch.clamp(ctx_noise, -self.config.noise_abs_max, self.config.noise_abs_max)
         t_ctx = torch.full((B, num_frames - 1), int(self.stabilization_level) - 1, dtype=torch.long, device=self.device)
         alpha_ctx = self.alphas_cumprod[t_ctx]
         x_noisy[:, :-1] = alpha_ctx.sqrt() * x_noisy[:, :-1] + (1 - alpha_ctx).sqrt() * ctx_noise
-        new_frame = torch.randn((B, 1, *x_noisy.shape[2:]), device=self.device, generator=generator)
+        new_frame = noise[:, -1:] if noise is not None else torch.randn((B, 1, *x_noisy.shape[2:]), device=self.device, generator=generator)
         x_noisy[:, -1:] = torch.clamp(new_frame, -self.config.noise_abs_max, self.config.noise_abs_max)
         start_frame = max(0, num_frames - self.dit.max_frames)
         v_pred = None

@@ -132,10 +132,13 @@ void gtav_dit_destroy(gtav_dit_t h);
 int gtav_dit_mod_width(gtav_dit_t h);
 
 /* A plan fixes (B, T) and owns the TMA descriptors for a caller-provided workspace.
- * cond_rows = rows of the conditioning table (B*T for a plain forward). */
+ * cond_rows = rows of the conditioning table (B*T for a plain forward).
+ * stream: the stream the plan's passes will be enqueued on - the split-K rendezvous counters inside the workspace are
+ * cleared with a cudaMemsetAsync on it, i.e. ordered after whatever used that (possibly recycled) memory before and
+ * before the plan's first kernel. */
 size_t gtav_dit_workspace_bytes(gtav_dit_t h, int B, int T, int cond_rows);
 int gtav_dit_plan_create(gtav_dit_t h, int B, int T, int cond_rows, void* workspace, size_t workspace_bytes,
-                         gtav_dit_plan_t* out);
+                         gtav_stream_t stream, gtav_dit_plan_t* out);
 void gtav_dit_plan_destroy(gtav_dit_plan_t p);
 
 /* Conditioning table: SiLU(t_embedder(t) + external_cond(a)) -> all adaLN modulation vectors

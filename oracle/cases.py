@@ -39,3 +39,15 @@ def seeded_rand(shape, seed):
 def subsample_image(img: torch.Tensor, stride: int = 8) -> torch.Tensor:
     """[N,3,H,W] -> every `stride`-th pixel, fp32 (keeps the decode goldens small)."""
     return img[:, :, ::stride, ::stride].float()
+
+
+# ---- full-size cases (oracle/make_golden_full.py): the BASELINE configs themselves, depth-16 DiT + VAE 6/12 ----------
+# C1 = BASELINE config 1 exactly: B=1, 360x640, dummy blue->red prompt (4 frames), 8 frames, 10 DDIM steps (11 DiT
+# evaluations per frame, generate.py:206), minted for the non-degenerate weights ("initB") and for zero adaLN linears
+# ("initA": every block an identity, like the reference's default init).
+C1 = dict(depth=16, enc_depth=6, dec_depth=12, n_prompt=4, total_frames=8, noise_steps=10, actions=False, seed=51)
+# One denoise_step of BASELINE config 3's shape: B=8 action-conditioned rollouts, full 5-frame window (M = 5760 rows).
+C3_STEP = dict(depth=16, B=8, frames=5, start_frame=0, noise_steps=100, noise_idx=57, actions=True, seed=52)
+# DiffusionTrainer.predict / predict_noise of the reference (train_dit.py:373-552) on the small models of ROLLOUT.
+TRAINER = dict(depth=2, enc_depth=1, dec_depth=1, ddim_noise_steps=16, ddim_noise_steps_inference=4, n_prompt_frames=2,
+               num_frames=6, noise_abs_max=20.0, seed_predict=61, seed_predict_noise=62)

@@ -105,4 +105,5 @@ def load():
         sys.modules.update(saved)
     return types.SimpleNamespace(DiT=rdit.DiT, AutoencoderKL=rvae.AutoencoderKL,
                                  denoise_step=rtrain.denoise_step,
-                                 sigmoid_beta_schedule=rutils.sigmoid_beta_schedule)
+                                 sigmoid_beta_schedule=rutils.sigmoid_beta_schedule,
+                                 train_module=rtrain)

@@ -31,8 +31,12 @@ SCALING_FACTOR = 0.07843137255  # reference generate.py:51,241
 @dataclass(frozen=True)
 class Rounding:
     """bf16=False: exact fp32 everywhere (what the reference computes on CPU).
-    bf16=True : round to bf16 wherever CUDA autocast would (SURVEY.md §3.3 numerics note)."""
+    bf16=True : round to bf16 wherever CUDA autocast would (SURVEY.md §3.3 numerics note).
+    sdpa=True : attention through F.scaled_dot_product_attention like the reference (model/attention.py:62,127) instead
+                of the explicit softmax - used with tensors on a CUDA device under torch.autocast(bf16) to time the
+                reference's own eager graph (cuBLAS + SDPA) on the GPU (bench.py: gpu_eager_baseline)."""
     bf16: bool = False
+    sdpa: bool = False
 
     def r(self, x: torch.Tensor) -> torch.Tensor:
         return x.to(torch.bfloat16).to(torch.float32) if self.bf16 else x
@@ -40,6 +44,7 @@ class Rounding:
 
 FP32 = Rounding(False)
 BF16 = Rounding(True)
+EAGER = Rounding(False, True)
 
 
 def _linear(rd: Rounding, x, w, b=None):
@@ -96,7 +101,7 @@ def denoise_step(sd, cfg: DiTConfig, x_noisy, actions, noise_idx, stabilization_
     """One sampler step (reference train_dit.py:30-125): context frames at t=stabilization_level,
     last frame at levels[noise_idx]; returns (x_pred, v_pred) for the window."""
     B, F_all = x_noisy.shape[:2]
-    t = torch.full((B, F_all), stabilization_level, dtype=torch.long)
+    t = torch.full((B, F_all), stabilization_level, dtype=torch.long, device=x_noisy.device)
     t_next = t.clone()
     t[:, -1] = levels[noise_idx]
     t_next[:, -1] = levels[max(0, noise_idx - 1)]
@@ -110,10 +115,12 @@ def denoise_step(sd, cfg: DiTConfig, x_noisy, actions, noise_idx, stabilization_
 
 
 def rollout(dit_sd, dcfg: DiTConfig, prompt_latents, actions, total_frames, noise_steps, noise_fn,
-            stabilization_level=15, noise_abs_max=20.0, rd: Rounding = FP32, on_step=None):
+            stabilization_level=15, noise_abs_max=20.0, rd: Rounding = FP32, on_step=None, abar=None):
     """Autoregressive loop of reference generate.py:192-220.  `noise_fn(i)` returns the [B,1,C,H,W]
-    Gaussian draw for frame i (the caller owns the RNG so product and oracle see the same noise)."""
-    abar = alphas_cumprod_table()
+    Gaussian draw for frame i (the caller owns the RNG so product and oracle see the same noise).
+    abar: the cumulative-alpha table; default generate.py's (clamp_min 1e-4) - DiffusionTrainer.predict runs the same
+    loop on its clamp_min 1e-6 table (train_dit.py:297-307, 400-450)."""
+    abar = alphas_cumprod_table() if abar is None else abar
     levels = noise_levels(noise_steps)
     x = prompt_latents.float()
     n_prompt = x.shape[1]
@@ -139,14 +146,14 @@ def _interleave2(a):  # "... n -> ... (n r)", r=2
 def axial_angles(base: torch.Tensor, h: int, w: int) -> torch.Tensor:
     """[h, w, 4*len(base)] angle table of `get_axial_freqs(h, w)` for freqs_for="pixel": positions
     linspace(-1,1,n) per axis, each angle repeated twice, row angles first then column angles."""
-    ah = _interleave2(torch.linspace(-1, 1, h)[:, None] * base[None])
-    aw = _interleave2(torch.linspace(-1, 1, w)[:, None] * base[None])
+    ah = _interleave2(torch.linspace(-1, 1, h, device=base.device)[:, None] * base[None])
+    aw = _interleave2(torch.linspace(-1, 1, w, device=base.device)[:, None] * base[None])
     return torch.cat([ah[:, None].expand(h, w, -1), aw[None].expand(h, w, -1)], dim=-1)
 
 
 def temporal_angles(base: torch.Tensor, T: int) -> torch.Tensor:
     """[T, 2*len(base)] table of `rotate_queries_or_keys`: window-relative positions arange(T)."""
-    return _interleave2(torch.arange(T, dtype=torch.float32)[:, None] * base[None])
+    return _interleave2(torch.arange(T, dtype=torch.float32, device=base.device)[:, None] * base[None])
 
 
 def apply_rotary(rd: Rounding, ang: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
@@ -163,10 +170,12 @@ def _attention(rd: Rounding, q, k, v, causal: bool):
     """softmax(q k^T / sqrt(d)) v; fp32 softmax, probabilities rounded before the second product
     when emulating the bf16 SDPA (reference calls F.scaled_dot_product_attention,
     model/attention.py:62,127; model/vae.py:101)."""
+    if rd.sdpa:
+        return F.scaled_dot_product_attention(q, k, v, is_causal=causal)
     s = (q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(q.shape[-1]))
     if causal:
         n = s.shape[-1]
-        s = s.masked_fill(torch.ones(n, n, dtype=torch.bool).triu(1), float("-inf"))
+        s = s.masked_fill(torch.ones(n, n, dtype=torch.bool, device=s.device).triu(1), float("-inf"))
     p = torch.softmax(s, dim=-1)
     return rd.r(rd.r(p) @ v)
 
@@ -177,7 +186,7 @@ def _attention(rd: Rounding, q, k, v, causal: bool):
 def timestep_embedding(t: torch.Tensor, dim: int = 256, max_period: float = 10000.0):
     """[cos(t f), sin(t f)] with f = exp(-ln(max_period) * arange(half)/half) (model/dit.py:95-118)."""
     half = dim // 2
-    f = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    f = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     a = t[:, None].float() * f[None]
     return torch.cat([a.cos(), a.sin()], dim=-1)
 

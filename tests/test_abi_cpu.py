@@ -33,7 +33,7 @@ def test_library_exports_exactly_the_header(native):
     out = subprocess.run(["nm", "-D", "--defined-only", native.LIB_PATH], capture_output=True, text=True).stdout
     exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l)
     assert exported == decl, set(exported) ^ set(decl)          # nothing else leaks out of the .so
-    assert lib.gtav_abi_version() == 2
+    assert lib.gtav_abi_version() == 3
 
 
 def test_library_is_sm100a_tcgen05(native):
@@ -151,3 +151,29 @@ def test_frame_stream_contract_cpu():
     import inspect
     assert list(inspect.signature(FrameStream.next).parameters) == ["self", "action", "noise", "decode"]
     assert callable(Sampler.stream)
+
+
+def test_modules_built_under_inference_mode_have_a_signature():
+    """The reference's generate.py builds and moves both models under @torch.inference_mode (load_models / main): their
+    parameters are inference tensors, which have no version counter - the pack signature must not touch it."""
+    import torch
+    from gtav_b200.model.dit import DiT
+    from gtav_b200.model.vae import AutoencoderKL
+    with torch.inference_mode():
+        dit = DiT(depth=1)
+        vae = AutoencoderKL(latent_dim=16, patch_size=20, enc_dim=1024, enc_depth=1, enc_heads=16, dec_dim=1024, dec_depth=1,
+                            dec_heads=16, input_height=360, input_width=640)
+        assert all(p.is_inference() for p in dit.parameters())
+        s1, s2 = dit._signature(), vae._signature()
+        assert len(s1) == len(list(dit.parameters())) and len(s2) == len(list(vae.parameters()))
+        assert all(v == -1 for _, v in s1)
+        # load_state_dict and .to() mark the packed copies stale even where no version counter can show it
+        assert not dit._dirty
+        dit.load_state_dict(dit.state_dict())
+        assert dit._dirty
+    vae._dirty = False
+    vae.to(torch.float32)
+    assert vae._dirty
+    dit._dirty = False
+    dit.repack()
+    assert dit._dirty

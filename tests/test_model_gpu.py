@@ -79,10 +79,9 @@ def test_dit_forward_bf16_input_and_replan():
 
 
 LAST_FRAME_MODES = {
-    # name: (GTAV_SKINNY, GTAV_MEGA, max-abs bound vs the dense window)
-    "tiled": ("0", "0", 0.0),        # same kernels, same arithmetic per row: bit-identical
-    "skinny": ("1", "0", 2e-2),      # weight-streaming GEMM: fp32 summation order inside the K splits differs
-    "step_kernel": ("1", "1", 3e-2), # persistent step kernel (B = 1): + LayerNorm statistics merged from 8 partials
+    # name: (GTAV_SKINNY, max-abs bound vs the dense window)
+    "tiled": ("0", 0.0),        # same kernels, same arithmetic per row: bit-identical
+    "skinny": ("1", 2e-2),      # weight-streaming GEMM: fp32 summation order inside the K splits differs
 }
 
 
@@ -90,9 +89,8 @@ LAST_FRAME_MODES = {
 def test_dit_last_frame_split_equals_dense(monkeypatch, mode):
     """Context pass + last-frame-only pass (the sampler's frame cache) == the last frame of the dense forward."""
     from gtav_b200.model.dit import DiT
-    skinny, mega, bound = LAST_FRAME_MODES[mode]
+    skinny, bound = LAST_FRAME_MODES[mode]
     monkeypatch.setenv("GTAV_SKINNY", skinny)
-    monkeypatch.setenv("GTAV_MEGA", mega)
     sd = make_dit_state(DiTConfig(depth=2), seed=0)
     model = DiT(depth=2)
     model.load_state_dict(sd, strict=True)
@@ -119,7 +117,6 @@ def test_fused_reduce_equals_separate_kernels(monkeypatch):
     for fuse in ("1", "0"):
         monkeypatch.setenv("GTAV_FUSE", fuse)
         monkeypatch.setenv("GTAV_SKINNY", "1")
-        monkeypatch.setenv("GTAV_MEGA", "0")
         model = DiT(depth=3)
         model.load_state_dict(sd, strict=True)
         model = model.cuda().eval()
@@ -135,11 +132,9 @@ def test_fused_reduce_equals_separate_kernels(monkeypatch):
         assert torch.equal(a, b), f"case {i}: fused reduce differs from separate kernels, max-abs {float((a.float() - b.float()).abs().max())}"
 
 
-@pytest.mark.parametrize("mega", ["1", "0"])
-def test_step_kernel_full_depth_vs_reference_golden(golden, monkeypatch, mega):
-    """The persistent step kernel on the real 16-block DiT (B = 1, T = 5): last frame of the v-prediction against the
-    unmodified reference's fp32 output, same tolerance as the dense forward."""
-    monkeypatch.setenv("GTAV_MEGA", mega)
+def test_last_frame_pass_full_depth_vs_reference_golden(golden):
+    """The frame-cache split (context pass + weight-streaming last-frame pass) on the real 16-block DiT (B = 1, T = 5): last
+    frame of the v-prediction against the unmodified reference's fp32 output, same tolerance as the dense forward."""
     from gtav_b200.model.dit import DiT
     c = CASES_DIT["d16_b1_t5_act"]
     sd = make_dit_state(DiTConfig(depth=16), seed=0)
@@ -150,7 +145,7 @@ def test_step_kernel_full_depth_vs_reference_golden(golden, monkeypatch, mega):
     t = torch.tensor(c["t"]).reshape(1, 5)
     a = w_key_actions(1, 5)
     v_last = model.forward_last_frame(x.cuda(), t.cuda(), a.cuda())
-    check(v_last, golden("dit_forward")["d16_b1_t5_act.v"][:, -1:], TOL_FP32, f"last-frame pass (step kernel={mega}), depth 16, vs reference fp32 golden")
+    check(v_last, golden("dit_forward")["d16_b1_t5_act.v"][:, -1:], TOL_FP32, "last-frame pass, depth 16, vs reference fp32 golden")
 
 
 def test_dit_rejects_cpu_and_bad_shapes():
@@ -202,11 +197,11 @@ def test_vae(golden, name):
     mean = vae.encode(img.cuda()).mean
     assert mean.dtype == torch.bfloat16 and mean.shape == (c["N"], 576, 16)
     # latents have std 1.4; bf16 through up to 6 blocks
-    check(mean, g[f"{name}.mean"], (1.5e-1, 2e-2), f"{name} encode mean vs reference fp32")
+    check(mean, g[f"{name}.mean"], (8e-2, 1e-2), f"{name} encode mean vs reference fp32")      # measured 0.051
     z = seeded_randn((c["N"], 576, 16), c["seed"] + 1)
     dec = vae.decode(z.cuda())
     assert dec.dtype == torch.bfloat16 and dec.shape == (c["N"], 3, 360, 640)
-    check(subsample_image(dec), g[f"{name}.dec_sub"], (1.5e-1, 2e-2), f"{name} decode vs reference fp32")
+    check(subsample_image(dec), g[f"{name}.dec_sub"], (6e-2, 1e-2), f"{name} decode vs reference fp32")   # measured 0.037
     if c["enc_depth"] == 1:
         cfg = VAEConfig(enc_depth=1, dec_depth=1)
         check(mean, rp.vae_encode_mean(sd, cfg, img, rp.BF16), (6e-2, 6e-3), f"{name} encode vs bf16 oracle")
@@ -232,8 +227,8 @@ def test_vae_posterior_moments(golden):
     c = CASES_VAE["e1_d1"]
     gp = golden("vae_posterior")
     pg = vae.encode((seeded_rand((c["N"], 3, 360, 640), c["seed"]) * 2 - 1).cuda())
-    check(pg.mean, gp["moments"][..., :16], (1.5e-1, 2e-2), "posterior mean vs reference fp32")
-    check(pg.logvar, gp["logvar"], (1.5e-1, 2e-2), "posterior logvar vs reference fp32")
+    check(pg.mean, gp["moments"][..., :16], (8e-2, 1e-2), "posterior mean vs reference fp32")
+    check(pg.logvar, gp["logvar"], (8e-2, 1e-2), "posterior logvar vs reference fp32")
     img = seeded_rand((2, 3, 360, 640), 97) * 2 - 1
     post = vae.encode(img.cuda())
     mom = rp.vae_encode_moments(sd, cfg, img, rp.BF16)
