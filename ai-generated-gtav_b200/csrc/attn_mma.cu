@@ -8,6 +8,8 @@
 // mma.sync m16n8k16 tiles (flash-style: scores stay in registers, online softmax across key
 // blocks, P rounded to bf16 before P@V like the reference's fused SDPA backends).  q/k are rotated
 // in fp32 and rounded to bf16 once, as apply_rotary_emb does (rotary_embedding_torch.py:46-73).
+#include <stdlib.h>
+
 #include "attn_seq.cuh"
 
 namespace gtav {
@@ -45,9 +47,20 @@ attn_seq144_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int hea
     attn_seq_body<144, 144, 3, 32, false>(qkv, out, heads, sRot, sK, sV, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, 0);
 }
 
+// GTAV_ATTN = "tc" (default): both shapes on the tcgen05 kernel (attn_tc.cu); "mma": the mma.sync kernels of this file
+// (kept for A/B measurements and as the independent implementation the parity tests compare against); "vae": tcgen05
+// for S = 576 only.
+static int attn_tc_mode() {
+    const char* e = getenv("GTAV_ATTN");          // read per call: launches are captured into graphs, tests flip it
+    return (e == nullptr || e[0] == 't') ? 2 : (e[0] == 'v' ? 1 : 0);
+}
+
 int launch_attention_seq(const bf16* qkv, bf16* out, int groups, int seq, int heads, const float2* rot, int rot_pairs,
                          cudaStream_t s) {
     if (groups <= 0) return 0;
+    const int tc = attn_tc_mode();
+    if ((tc == 2 && seq == 144 && rot_pairs == 32) || (tc >= 1 && seq == 576 && rot_pairs == 16))
+        return launch_attention_tc(qkv, out, groups, seq, heads, rot, rot_pairs, s);
     if (seq == 144 && rot_pairs == 32) {
         // all 144 keys of a head staged in one pass (every global load of the block in flight at once); the queries
         // are split over 3 CTAs of 3 warps so that 48 SMs share the loads at B = 1

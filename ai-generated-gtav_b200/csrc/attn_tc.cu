@@ -1,0 +1,512 @@
+// Non-causal multi-head attention over short sequences on the 5th-generation tensor cores, rotary embedding fused
+// into the operand staging.
+//
+// Replaces SpatialAxialAttention's rearrange + get_axial_freqs + apply_rotary_emb + SDPA (reference
+// model/attention.py:99-129: S = 144 tokens per frame, rotary on all 64 head dims) and the VAE Attention
+// (reference model/vae.py:78-107: S = 576, rotary on head dims 0..31 only).  Head dim 64; one CTA per (sequence, head).
+//
+//   * K and V of the whole head are brought ONCE into shared memory with cp.async (all copies of a thread in flight
+//     together) as 128-byte-swizzled rows of 64 bf16; K is then rotated in place (fp32 math, one bf16 rounding -
+//     apply_rotary_emb, rotary_embedding_torch.py:46-73).  K is the K-major B operand of S = Q K^T, the same kind of
+//     image of V is the MN-major B operand of O = P V (no transpose anywhere);
+//   * queries are processed in tiles of 128 rows (UMMA M = 128), staged the same way by two loader warps into a
+//     double-buffered slot while the previous tile is being worked on;
+//   * the (query tile, key block) pairs form ONE flat sequence n = 0, 1, ...: the MMA thread issues S(n + 1) = Q K^T
+//     into the double-buffered TMEM S region before the P V product of block n, and the two softmax warpgroups take the
+//     blocks alternately (warps 0-3 the even n, warps 4-7 the odd n; thread = query row = TMEM lane), so that one
+//     group's TMEM loads, shared-memory stores and barrier waits run under the other group's exponentials - the MUFU
+//     pipe (one ex2 per score, 16 per clock per SM) is the bound of this kernel;
+//   * softmax across key blocks is the online one with LAZY rescaling: a block adopts the previous blocks' row
+//     maximum unless its own exceeds it by more than 2^8 (probabilities then stay below 256, harmless in fp32 / bf16);
+//     only then are the row's partial O (tcgen05.ld / st) and row sum rescaled - with bounded logits that is rare.  The
+//     result is the exact softmax (every probability of a row is scaled by the same factor);
+//   * probabilities are rounded to bf16 like the reference's fused SDPA backends and written straight back into TENSOR
+//     MEMORY with tcgen05.st, over the S columns they were computed from (two bf16 per 32-bit column, row = lane): the
+//     second product takes its A operand P from TMEM (tcgen05.mma [d], [a], b-desc), so the probabilities never touch
+//     shared memory - no 48 KB staging buffer, no generic -> async proxy fence, and the softmax threads stream
+//     load -> exp -> store 32 columns at a time without holding a whole row in registers;
+//   * O [128 x 64] accumulates in TMEM (double-buffered across query tiles) and is normalised by the fp32 row sum in
+//     the epilogue;
+//   * every hand-off is an mbarrier (tcgen05.commit on the tensor side); no CTA-wide barrier inside the loop.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gtav {
+
+namespace {
+
+constexpr int AT_GROUP_WARPS = 4;                     // one softmax warpgroup = 128 query rows
+constexpr int AT_SOFTMAX_WARPS = 2 * AT_GROUP_WARPS;
+constexpr int AT_LOADER_WARPS = 2;
+constexpr int AT_THREADS = (AT_SOFTMAX_WARPS + 1 + AT_LOADER_WARPS) * 32;      // 352
+constexpr int AT_QTILE = 128;
+constexpr int AT_ROWB = 128;                          // bytes per staged row (64 bf16)
+constexpr float AT_LAZY = 8.0f;                       // rescale only when the maximum grows by more than 2^8
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+          "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+          "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]: A = 128 lanes (rows) x 16 bf16 (8 columns of 32 bits) starting at tmem_a
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+// rotate the adjacent pair packed in `u` by (cos, sin) and re-round to bf16 (fp32 math, one rounding)
+__device__ __forceinline__ uint32_t rot_pair(uint32_t u, float2 cs) {
+    const float2 x = unpack_bf16x2(u);
+    return pack_bf16x2(x.x * cs.x - x.y * cs.y, x.y * cs.x + x.x * cs.y);
+}
+// byte offset of chunk c of row r inside a [rows][128 B] image with the 128-byte swizzle (chunk index ^ row % 8)
+__device__ __forceinline__ uint32_t sw128(int r, int c) { return static_cast<uint32_t>(r) * AT_ROWB + ((c ^ (r & 7)) << 4); }
+// Copy chunk c (16 bytes = 8 features) of rows r0, r0 + RSTRIDE, ... (< n_rows of the image; sequence position pos0 + row,
+// rows at positions >= seq are zero-filled) from global memory into the swizzled image with cp.async - every copy of
+// the thread in flight at once - and rotate the chunks that carry rotary pairs in place.  The rotary angles of a batch
+// of rows are fetched into registers while the copies are in flight (fetched row by row after the wait, each was an
+// exposed L2 round trip: 4 us per 128-row tile).  A thread only ever touches chunks it copied itself, so no barrier is
+// needed between the copy and the rotation.  src2 / img2: optional second matrix copied alongside without rotation (V).
+template <int ROT_PAIRS, int RSTRIDE, int MAXROWS, int RB>
+__device__ __forceinline__ void stage_rows(uint8_t* img, const bf16* src, uint8_t* img2, const bf16* src2, int ld, int r0, int c,
+                                           int n_rows, int pos0, int seq, const float2* __restrict__ rot) {
+    for (int r = r0; r < n_rows; r += RSTRIDE) {
+        const bool ok = pos0 + r < seq;
+        const size_t goff = ok ? static_cast<size_t>(pos0 + r) * ld + c * 8 : 0;
+        cp_async16(img + sw128(r, c), src + goff, ok ? 16 : 0);
+        if (img2 != nullptr) cp_async16(img2 + sw128(r, c), src2 + goff, ok ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (c * 4 < ROT_PAIRS) {
+#pragma unroll 1
+        for (int k0 = 0; k0 < MAXROWS; k0 += RB) {
+            float4 tb[RB][2];
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+                const int r = r0 + (k0 + i) * RSTRIDE;
+                if (r < n_rows && pos0 + r < seq) {
+                    const float4* tp = reinterpret_cast<const float4*>(rot + (pos0 + r) * ROT_PAIRS + c * 4);
+                    tb[i][0] = tp[0];
+                    tb[i][1] = tp[1];
+                }
+            }
+            if (k0 == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+                const int r = r0 + (k0 + i) * RSTRIDE;
+                if (r < n_rows && pos0 + r < seq) {
+                    uint4* p = reinterpret_cast<uint4*>(img + sw128(r, c));
+                    uint4 w = *p;
+                    w.x = rot_pair(w.x, make_float2(tb[i][0].x, tb[i][0].y));
+                    w.y = rot_pair(w.y, make_float2(tb[i][0].z, tb[i][0].w));
+                    w.z = rot_pair(w.z, make_float2(tb[i][1].x, tb[i][1].y));
+                    w.w = rot_pair(w.w, make_float2(tb[i][1].z, tb[i][1].w));
+                    *p = w;
+                }
+            }
+        }
+    } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+}
+
+// kind::f16 instruction descriptor with an MN-major B operand (bit 16): V staged as [key][64 dims]
+__host__ __device__ constexpr uint32_t idesc_bf16_bmn(int m, int n) { return umma_idesc_bf16(m, n) | (1u << 16); }
+
+template <int SEQ, int KB>
+struct AttnCfg {
+    static constexpr int NKB = SEQ / KB;                               // key blocks per query tile
+    static constexpr int QTILES = (SEQ + AT_QTILE - 1) / AT_QTILE;
+    static constexpr int NBLK = QTILES * NKB;                          // length of the flat (tile, block) sequence
+    static constexpr int KV_BYTES = SEQ * AT_ROWB;
+    static constexpr int Q_BYTES = AT_QTILE * AT_ROWB;                 // 16 KB
+    static constexpr int OFF_V = KV_BYTES;
+    static constexpr int OFF_Q = 2 * KV_BYTES;
+    static constexpr int OFF_M = OFF_Q + 2 * Q_BYTES;                  // running row maximum handed from block to block
+    static constexpr int OFF_L = OFF_M + AT_QTILE * 4;                 // (row sum, its reference maximum) of the non-final group
+    static constexpr int OFF_BAR = OFF_L + AT_QTILE * 8;
+    static constexpr int SMEM = OFF_BAR + 192 + 1024;                  // + alignment slack
+    static constexpr int S_COLS = KB;                                  // TMEM columns: S0 | S1 | O0 | O1; P(n) overwrites S(n)[0, KB/2)
+    static constexpr int TM_O = 2 * S_COLS;
+    static constexpr int TM_COLS = 512;
+    static_assert(SEQ % KB == 0 && KB % 16 == 0 && KB <= 256 && (KB % 64 == 0 || KB % 64 == 16), "key blocking");
+    static_assert(NKB == 1 || NKB % 2 == 1, "the row-sum hand-off buffer relies on the groups swapping roles every tile");
+    static_assert((KB * AT_ROWB) % 1024 == 0, "key blocks must start on a swizzle-atom boundary");
+    static_assert(2 * S_COLS + 128 <= 512, "TMEM budget");
+    static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+// barrier slots
+// (S_FREE[b]: committed by the tensor core after the P V product that read P out of S buffer b)
+// Every barrier that a producer could complete twice before its consumer has looked (a parity wait cannot tell phase k
+// from phase k + 2) exists once per S buffer / tile parity, so that the producer's next arrival depends on the consumer.
+enum { B_QFULL = 0, B_QFREE = 2, B_SFULL = 4, B_SFREE = 6, B_PREADY = 8, B_OFULL = 10, B_OFREE = 12, B_MREADY = 14,
+       B_LREADY = 15, B_DBG = 16, B_COUNT = 17 };
+
+template <int SEQ, int KB, int ROT_PAIRS>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, const float2* __restrict__ rot, long long* trace) {
+    using C = AttnCfg<SEQ, KB>;
+    // optional phase trace (profiling aid, null in production): [cta][role 0 softmax A / 1 mma / 2 loader / 3 softmax B][64] ns
+    int n_stamp = 0;
+#define AT_STAMP(role)                                                                                          \
+    do {                                                                                                        \
+        if (trace != nullptr && n_stamp < 64) {                                                                 \
+            long long t__;                                                                                      \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                                            \
+            trace[(static_cast<size_t>(blockIdx.x) * 4 + (role)) * 64 + n_stamp++] = t__;                       \
+        }                                                                                                       \
+    } while (0)
+    extern __shared__ uint8_t smem_raw[];
+    // (offset arithmetic on the __shared__ array itself: the compiler keeps the address space and emits LDS / STS - a
+    // pointer rebuilt from an integer made every shared access a generic LD / ST with long-scoreboard stalls)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sK = smem;
+    uint8_t* sV = smem + C::OFF_V;
+    uint8_t* sQ = smem + C::OFF_Q;
+    float* sM = reinterpret_cast<float*>(smem + C::OFF_M);
+    float2* sL = reinterpret_cast<float2*>(smem + C::OFF_L);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int head = blockIdx.x % heads, group = blockIdx.x / heads;
+    const int ld = 3 * heads * 64;
+    const size_t row_base = static_cast<size_t>(group) * SEQ;
+    const bf16* qbase = qkv + row_base * ld + head * 64;
+    const bf16* kbase = qbase + heads * 64;
+    const bf16* vbase = kbase + heads * 64;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[B_QFULL], AT_LOADER_WARPS * 32); mbar_init(&bars[B_QFULL + 1], AT_LOADER_WARPS * 32);
+        mbar_init(&bars[B_QFREE], 1); mbar_init(&bars[B_QFREE + 1], 1);
+        mbar_init(&bars[B_SFULL], 1); mbar_init(&bars[B_SFULL + 1], 1);
+        mbar_init(&bars[B_SFREE], 1); mbar_init(&bars[B_SFREE + 1], 1);
+        mbar_init(&bars[B_PREADY], AT_GROUP_WARPS * 32); mbar_init(&bars[B_PREADY + 1], AT_GROUP_WARPS * 32);
+        mbar_init(&bars[B_OFULL], 1); mbar_init(&bars[B_OFULL + 1], 1);
+        mbar_init(&bars[B_OFREE], AT_GROUP_WARPS * 32); mbar_init(&bars[B_OFREE + 1], AT_GROUP_WARPS * 32);
+        mbar_init(&bars[B_MREADY], AT_GROUP_WARPS * 32);
+        mbar_init(&bars[B_LREADY], AT_GROUP_WARPS * 32);
+        mbar_init(&bars[B_DBG], 1);
+        fence_barrier_init();
+    }
+    if (warp == AT_SOFTMAX_WARPS) {
+        tmem_alloc(tmem_slot, C::TM_COLS);
+        tmem_relinquish();
+    }
+    pdl_trigger();
+    if (threadIdx.x == 0) AT_STAMP(0);             // entry
+    pdl_wait();                                    // qkv is the previous kernel's output
+
+    // ---- K and V of the whole head -> shared memory.  Thread i copies chunk (i % 8) of rows i / 8, i / 8 + 44, ...
+    // (352 threads = 44 rows per sweep), so it later rotates exactly the K chunks it copied itself: no barrier
+    // between the copy and the rotation.
+    {
+        constexpr int RS = AT_THREADS / 8, MAXR = (SEQ + RS - 1) / RS;
+        stage_rows<ROT_PAIRS, RS, MAXR, (MAXR + 1) / 2>(sK, kbase, sV, vbase, ld, threadIdx.x >> 3, threadIdx.x & 7, SEQ, 0, SEQ, rot);
+    }
+    fence_proxy_async_smem();                      // generic-proxy stores -> visible to the tensor core's async proxy
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) AT_STAMP(0);             // K / V staged
+
+    if (warp < AT_SOFTMAX_WARPS) {
+        // =========================================================================== softmax + epilogue warpgroups
+        const int grp = warp >> 2, q = warp & 3;                         // group 0: even blocks, group 1: odd blocks
+        const int row = q * 32 + lane;                                   // row of the query tile = TMEM lane
+        const bool tr = trace != nullptr && lane == 0 && q == 0;
+        const int tr_role = grp == 0 ? 0 : 3;
+        const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const float sl2 = 0.125f * 1.4426950408889634f;                  // 1/sqrt(64) * log2(e)
+        const int ldo = heads * 64;
+        float l = 0.f, m_mine = -INFINITY;                               // this thread's share of the row sum, relative to m_mine
+#pragma unroll 1
+        for (int n = grp; n < C::NBLK; n += 2) {
+            const int t = n / C::NKB, j = n - t * C::NKB;
+            const uint32_t b = n & 1;                                    // == grp: this group always reads S buffer `grp`
+            mbar_wait(&bars[B_SFULL + b], (n >> 1) & 1);
+            tcgen05_fence_after();
+            if (tr) AT_STAMP(tr_role);                                   // S full
+            const uint32_t ta = tlane + b * C::S_COLS;
+            constexpr int FULL = KB / 64 * 64;                           // columns swept 64 at a time; 16-column tail (KB = 144)
+            // ---- row maximum of this block (first sweep over the S tile)
+            float bm = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < FULL; c += 64) {
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32(ta + c, v0);
+                tmem_ld_32x32(ta + c + 32, v1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) bm = fmaxf(bm, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+            }
+            if (FULL < KB) {
+                uint32_t v[16];
+                tmem_ld_32x16(ta + FULL, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) bm = fmaxf(bm, __uint_as_float(v[i]));
+            }
+            // ---- the maximum this row is expressed in: the previous block's, unless this block's exceeds it by > 2^8
+            float m_use = bm, o_scale = 1.0f;
+            if (n > 0) mbar_wait(&bars[B_MREADY], (n - 1) & 1);          // (every block waits: keeps the phases in step)
+            if (j > 0) {
+                const float m_prev = sM[row];
+                if ((bm - m_prev) * sl2 > AT_LAZY) o_scale = ex2_approx((m_prev - bm) * sl2);
+                else m_use = m_prev;
+            }
+            sM[row] = m_use;
+            mbar_arrive(&bars[B_MREADY]);
+            if (j <= 1) {                                                // this group's first block of the tile (blocks alternate)
+                l = 0.f;
+                m_mine = m_use;
+            }
+            if (m_use != m_mine) {                                       // the row's reference moved since this thread's last block
+                l *= ex2_approx((m_mine - m_use) * sl2);
+                m_mine = m_use;
+            }
+            if (j > 0 && __any_sync(0xffffffffu, o_scale != 1.0f)) {
+                // rare: this block raised the row maximum by more than 2^8 - rescale the row's partial output once the
+                // previous P V product has completed (its commit on S_FREE of the other buffer), before the next one
+                // accumulates onto it
+                mbar_wait(&bars[B_SFREE + (b ^ 1)], ((n - 1) >> 1) & 1);
+                tcgen05_fence_after();
+                const uint32_t to = tlane + C::TM_O + (t & 1) * 64;
+#pragma unroll
+                for (int c = 0; c < 64; c += 32) {
+                    uint32_t o[32];
+                    tmem_ld_32x32(to + c, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * o_scale);
+                    tmem_st_32x32(to + c, o);
+                }
+            }
+            // ---- exponentials (second sweep): 32 S columns in, 16 P columns (bf16 pairs) out, over the columns just read
+            const float mo = m_use * sl2;
+#pragma unroll
+            for (int c = 0; c < FULL; c += 32) {
+                uint32_t v[32], pk[16];
+                tmem_ld_32x32(ta + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float p0 = ex2_approx(__uint_as_float(v[i]) * sl2 - mo), p1 = ex2_approx(__uint_as_float(v[i + 1]) * sl2 - mo);
+                    l += p0 + p1;                                        // fp32 sum of the unrounded probabilities
+                    pk[i / 2] = pack_bf16x2(p0, p1);
+                }
+                tmem_st_32x16(ta + c / 2, pk);
+            }
+            if (FULL < KB) {
+                uint32_t v[16], pk[8];
+                tmem_ld_32x16(ta + FULL, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    const float p0 = ex2_approx(__uint_as_float(v[i]) * sl2 - mo), p1 = ex2_approx(__uint_as_float(v[i + 1]) * sl2 - mo);
+                    l += p0 + p1;
+                    pk[i / 2] = pack_bf16x2(p0, p1);
+                }
+                tmem_st_32x8(ta + FULL / 2, pk);
+            }
+            tmem_st_wait();
+            tcgen05_fence_before();
+            mbar_arrive(&bars[B_PREADY + b]);                            // P(n) is in tensor memory
+            if (tr) AT_STAMP(tr_role);                                   // P written
+            // ---- end of this group's work on the tile
+            if (C::NKB > 1 && j == C::NKB - 2) {                         // the OTHER group finishes the tile: hand it our share
+                sL[row] = make_float2(l, m_mine);
+                mbar_arrive(&bars[B_LREADY]);
+            }
+            if (j == C::NKB - 1) {
+                // epilogue of tile t: O / (row sum) -> bf16 -> out[row][head*64 ..]
+                float lt = l;
+                if (C::NKB > 1) {
+                    mbar_wait(&bars[B_LREADY], t & 1);
+                    const float2 o = sL[row];
+                    lt += o.x * ex2_approx((o.y - m_mine) * sl2);
+                }
+                const float inv = 1.0f / lt;
+                const uint32_t ob = t & 1;
+                mbar_wait(&bars[B_OFULL + ob], (t >> 1) & 1);
+                tcgen05_fence_after();
+                if (tr) AT_STAMP(tr_role);                               // O full
+                const int grow = t * AT_QTILE + row;
+                bf16* dst = out + (row_base + grow) * ldo + head * 64;
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t o[32];
+                    tmem_ld_32x32(tlane + C::TM_O + ob * 64 + c0, o);
+                    tmem_ld_wait();
+                    if (c0 == 32) {
+                        tcgen05_fence_before();
+                        mbar_arrive(&bars[B_OFREE + ob]);
+                    }
+                    if (grow < SEQ) {
+#pragma unroll
+                        for (int c = 0; c < 32; c += 8) {
+                            uint4 w;
+                            w.x = pack_bf16x2(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv);
+                            w.y = pack_bf16x2(__uint_as_float(o[c + 2]) * inv, __uint_as_float(o[c + 3]) * inv);
+                            w.z = pack_bf16x2(__uint_as_float(o[c + 4]) * inv, __uint_as_float(o[c + 5]) * inv);
+                            w.w = pack_bf16x2(__uint_as_float(o[c + 6]) * inv, __uint_as_float(o[c + 7]) * inv);
+                            *reinterpret_cast<uint4*>(dst + c0 + c) = w;
+                        }
+                    }
+                }
+                if (tr) AT_STAMP(tr_role);                               // tile stored
+            }
+        }
+    } else if (warp == AT_SOFTMAX_WARPS) {
+        // =========================================================================== MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = umma_idesc_bf16(AT_QTILE, KB);              // S = Q K^T: both operands K-major
+            constexpr uint32_t idesc_o = idesc_bf16_bmn(AT_QTILE, 64);               // O = P V: V MN-major
+            constexpr int PV_STEPS = KB / 16;
+            uint32_t n_dbg = 0;
+            const bool dbg_pv = false;
+            const uint64_t desc_q0 = umma_desc_sw128(smem_u32(sQ)), desc_k0 = umma_desc_sw128(smem_u32(sK));
+            const uint64_t desc_v0 = umma_desc_sw128(smem_u32(sV));
+            auto try_pv = [&](int n) -> bool {                   // O += P(n) V: needs P written (and, first block of a tile, O read out)
+                const int t = n / C::NKB, j = n - t * C::NKB;
+                if (j == 0 && t >= 2 && !mbar_try_wait(&bars[B_OFREE + (t & 1)], ((t >> 1) - 1) & 1)) return false;
+                if (!mbar_try_wait(&bars[B_PREADY + (n & 1)], (n >> 1) & 1)) return false;
+                tcgen05_fence_after();
+                AT_STAMP(1);                       // P ready
+                const uint32_t d = tmem_base + C::TM_O + (t & 1) * 64;
+                const uint32_t pa = tmem_base + (n & 1) * C::S_COLS;         // P(n): 8 columns per K step of 16 keys
+                // B descriptors = a base built once + compile-time offsets (16-byte units): the issuing thread's own scalar
+                // code is what bounds a short MMA (scripts/probe_umma_pv.cu: ~100 cycles per MMA with the descriptor
+                // rebuilt in the loop, ~61 with it precomputed)
+                const uint64_t db0 = desc_v0 + static_cast<uint64_t>(j * (KB * AT_ROWB / 16));
+#pragma unroll
+                for (int ks = 0; ks < PV_STEPS; ++ks)
+                    umma_bf16_ts(d, pa + ks * 8, db0 + ks * (16 * AT_ROWB / 16), idesc_o, (j | ks) != 0 ? 1u : 0u);
+                umma_commit(&bars[B_SFREE + (n & 1)]);                       // S buffer (and the P inside it) consumed
+                if (j == C::NKB - 1) umma_commit(&bars[B_OFULL + (t & 1)]);
+                if (trace != nullptr && dbg_pv) {  // profiling only (GTAV_ATTN_TRACE bit 0 of the address set): time the product itself
+                    umma_commit(&bars[B_DBG]);
+                    mbar_wait(&bars[B_DBG], n_dbg++ & 1);
+                    AT_STAMP(1);                   // P V done
+                }
+                return true;
+            };
+            auto try_s = [&](int n) -> bool {                    // S(n) = Q K^T: needs the query tile staged and the S buffer read out
+                const int t = n / C::NKB, j = n - t * C::NKB;
+                const uint32_t b = n & 1;
+                if (j == 0 && !mbar_try_wait(&bars[B_QFULL + (t & 1)], (t >> 1) & 1)) return false;
+                if (n >= 2 && !mbar_try_wait(&bars[B_SFREE + b], ((n >> 1) - 1) & 1)) return false;
+                tcgen05_fence_after();
+                const uint32_t d = tmem_base + b * C::S_COLS;
+                const uint64_t da0 = desc_q0 + static_cast<uint64_t>((t & 1) * (C::Q_BYTES / 16));
+                const uint64_t db0 = desc_k0 + static_cast<uint64_t>(j * (KB * AT_ROWB / 16));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16_ss(d, da0 + 2 * k, db0 + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+                umma_commit(&bars[B_SFULL + b]);
+                if (j == C::NKB - 1) umma_commit(&bars[B_QFREE + (t & 1)]);          // last read of this query tile
+                AT_STAMP(1);                       // S(n) issued
+                return true;
+            };
+            // Whichever of the two next products has its operands ready is issued, S first: the S tile of block n + 1 (and
+            // n + 2 as soon as its buffer has been read out) must not queue behind a P V product that is still waiting for
+            // its probabilities - the softmax group that owns the buffer would sit idle for that long.
+            int next_s = 0, next_pv = 0;
+            uint32_t idle = 0;
+            while (next_pv < C::NBLK) {
+                bool did = false;
+                if (next_s < C::NBLK && try_s(next_s)) { ++next_s; did = true; }
+                else if (next_pv < next_s && try_pv(next_pv)) { ++next_pv; did = true; }
+                if (did) idle = 0;
+                else if (++idle > (1u << 24)) { printf("gtav: attention MMA scheduler stalled (block %d)\n", blockIdx.x); __trap(); }
+            }
+        }
+    } else {
+        // =========================================================================== query-tile loaders
+        const int lt = threadIdx.x - (AT_SOFTMAX_WARPS + 1) * 32;        // 0 .. 63: chunk lt % 8 of rows lt / 8, lt / 8 + 8, ...
+        const int c = lt & 7;
+#pragma unroll 1
+        for (int t = 0; t < C::QTILES; ++t) {
+            if (t >= 2) mbar_wait(&bars[B_QFREE + (t & 1)], ((t >> 1) - 1) & 1);
+            if (lt == 0) AT_STAMP(2);              // slot free
+            uint8_t* dstq = sQ + (t & 1) * C::Q_BYTES;
+            constexpr int RS = AT_LOADER_WARPS * 4, MAXR = AT_QTILE / RS;
+            stage_rows<ROT_PAIRS, RS, MAXR, MAXR / 2>(dstq, qbase, nullptr, nullptr, ld, lt >> 3, c, AT_QTILE, t * AT_QTILE, SEQ, rot);
+            fence_proxy_async_smem();
+            mbar_arrive(&bars[B_QFULL + (t & 1)]);
+            if (lt == 0) AT_STAMP(2);              // staged
+        }
+    }
+    // ---- all roles done: the last tile's epilogue has read O, every MMA has completed (o_full was waited on)
+    tcgen05_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) AT_STAMP(0);             // end
+    if (warp == AT_SOFTMAX_WARPS) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, C::TM_COLS);
+    }
+#undef AT_STAMP
+}
+
+template <int SEQ, int KB, int ROT_PAIRS>
+int launch_tc(const bf16* qkv, bf16* out, int groups, int heads, const float2* rot, cudaStream_t s) {
+    using C = AttnCfg<SEQ, KB>;
+    static bool configured = false;
+    auto kern = attn_tc_kernel<SEQ, KB, ROT_PAIRS>;
+    if (!configured) {
+        GTAV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        configured = true;
+    }
+    long long* trace = nullptr;                    // GTAV_ATTN_TRACE=<device address of [CTAs][4][64] int64>: scripts/trace_attn.py
+    if (const char* e = getenv("GTAV_ATTN_TRACE")) trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
+    GTAV_CUDA_OK(launch_k(kern, dim3(groups * heads), dim3(AT_THREADS), C::SMEM, s, qkv, out, heads, rot, trace));
+    return 0;
+}
+
+}  // namespace
+
+// seq 576 / rot_pairs 16: VAE attention; seq 144 / rot_pairs 32: DiT spatial attention.
+int launch_attention_tc(const bf16* qkv, bf16* out, int groups, int seq, int heads, const float2* rot, int rot_pairs,
+                        cudaStream_t s) {
+    if (groups <= 0) return 0;
+    if (seq == 576 && rot_pairs == 16) return launch_tc<576, 192, 16>(qkv, out, groups, heads, rot, s);
+    if (seq == 144 && rot_pairs == 32) return launch_tc<144, 144, 32>(qkv, out, groups, heads, rot, s);
+    set_error("attention (tcgen05): unsupported (seq=%d, rot_pairs=%d); built for (144,32) and (576,16)", seq, rot_pairs);
+    return -1;
+}
+
+}  // namespace gtav

@@ -142,6 +142,9 @@ int launch_ln_affine(const bf16* x, bf16* out, int M, int D, const float* w, con
 // first 2*rot_pairs features of q and k.  seq must be 144 (DiT spatial) or 576 (VAE).
 int launch_attention_seq(const bf16* qkv, bf16* out, int groups, int seq, int heads, const float2* rot, int rot_pairs,
                          cudaStream_t s);
+// The same op on tcgen05 tensor cores (attn_tc.cu): S = Q K^T and O = P V as UMMA tiles with TMEM accumulators.
+int launch_attention_tc(const bf16* qkv, bf16* out, int groups, int seq, int heads, const float2* rot, int rot_pairs,
+                        cudaStream_t s);
 // Causal attention over the T frames of each (b, spatial position, head); rows ordered (b, t, pos).
 // rot: float2 [T][32] window-relative angles.  kv_cache (optional) [B*T*positions, 2*H*64]: receives the rotated
 // K and the V of every row, for later last-frame-only steps.

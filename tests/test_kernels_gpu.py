@@ -194,8 +194,11 @@ def _rotate(x, ang):
     return torch.cat([r16(head * a.cos() + sw * a.sin()), tail], dim=-1)
 
 
-@pytest.mark.parametrize("seq,pairs,groups", [(144, 32, 5), (576, 16, 2)])
-def test_attention_seq(lib, seq, pairs, groups):
+@pytest.mark.parametrize("impl", ["tc", "mma"])
+@pytest.mark.parametrize("seq,pairs,groups", [(144, 32, 5), (576, 16, 2), (576, 16, 11), (144, 32, 1)])
+def test_attention_seq(lib, monkeypatch, seq, pairs, groups, impl):
+    """impl tc: the tcgen05 kernel (attn_tc.cu, the default); mma: the mma.sync kernel it replaced (GTAV_ATTN=mma)."""
+    monkeypatch.setenv("GTAV_ATTN", impl)
     N = _N()
     H, d = 16, 64
     g = torch.Generator(device="cuda").manual_seed(seq)
