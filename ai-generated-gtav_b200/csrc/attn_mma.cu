@@ -47,19 +47,24 @@ attn_seq144_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int hea
     attn_seq_body<144, 144, 3, 32, false>(qkv, out, heads, sRot, sK, sV, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, 0);
 }
 
-// GTAV_ATTN = "tc" (default): both shapes on the tcgen05 kernel (attn_tc.cu); "mma": the mma.sync kernels of this file
-// (kept for A/B measurements and as the independent implementation the parity tests compare against); "vae": tcgen05
-// for S = 576 only.
-static int attn_tc_mode() {
+// Which implementation runs (measured on B200, scripts/bench_attn.py, profiles/r02/bench_attn_*.log):
+//   S = 576 (VAE): the tcgen05 kernel (attn_tc.cu) from 4 frames up (64 CTAs): 128 us against 222 us for 32 frames; below
+//                  that one CTA per head leaves most SMs idle and the mma.sync kernel's 9 CTAs per head win (23 vs 31 us);
+//   S = 144 (DiT): the tcgen05 kernel from 40 frames up (dense windows of 8 rollouts, context passes, 64-rollout steps),
+//                  where the two are within 5 % of each other (230 vs 238 us at 320 frames); the latency-bound last-frame
+//                  steps of few rollouts stay on the mma.sync kernel (5 us against 11 us per launch at one frame).
+// GTAV_ATTN = "tc" / "mma" forces one of them for every size (parity tests, A/B measurements).
+static int attn_use_tc(int seq, int groups) {
     const char* e = getenv("GTAV_ATTN");          // read per call: launches are captured into graphs, tests flip it
-    return (e == nullptr || e[0] == 't') ? 2 : (e[0] == 'v' ? 1 : 0);
+    if (e != nullptr && e[0] == 't') return 1;
+    if (e != nullptr && e[0] == 'm') return 0;
+    return seq == 576 ? groups >= 4 : groups >= 40;
 }
 
 int launch_attention_seq(const bf16* qkv, bf16* out, int groups, int seq, int heads, const float2* rot, int rot_pairs,
                          cudaStream_t s) {
     if (groups <= 0) return 0;
-    const int tc = attn_tc_mode();
-    if ((tc == 2 && seq == 144 && rot_pairs == 32) || (tc >= 1 && seq == 576 && rot_pairs == 16))
+    if (((seq == 144 && rot_pairs == 32) || (seq == 576 && rot_pairs == 16)) && attn_use_tc(seq, groups))
         return launch_attention_tc(qkv, out, groups, seq, heads, rot, rot_pairs, s);
     if (seq == 144 && rot_pairs == 32) {
         // all 144 keys of a head staged in one pass (every global load of the block in flight at once); the queries

@@ -146,7 +146,7 @@ __device__ __forceinline__ void stage_rows(uint8_t* img, const bf16* src, uint8_
 // kind::f16 instruction descriptor with an MN-major B operand (bit 16): V staged as [key][64 dims]
 __host__ __device__ constexpr uint32_t idesc_bf16_bmn(int m, int n) { return umma_idesc_bf16(m, n) | (1u << 16); }
 
-template <int SEQ, int KB>
+template <int SEQ, int KB, int NBUF, int TMC>
 struct AttnCfg {
     static constexpr int NKB = SEQ / KB;                               // key blocks per query tile
     static constexpr int QTILES = (SEQ + AT_QTILE - 1) / AT_QTILE;
@@ -156,30 +156,43 @@ struct AttnCfg {
     static constexpr int OFF_V = KV_BYTES;
     static constexpr int OFF_Q = 2 * KV_BYTES;
     static constexpr int OFF_M = OFF_Q + 2 * Q_BYTES;                  // running row maximum handed from block to block
-    static constexpr int OFF_L = OFF_M + AT_QTILE * 4;                 // (row sum, its reference maximum) of the non-final group
-    static constexpr int OFF_BAR = OFF_L + AT_QTILE * 8;
-    static constexpr int SMEM = OFF_BAR + 192 + 1024;                  // + alignment slack
-    static constexpr int S_COLS = KB;                                  // TMEM columns: S0 | S1 | O0 | O1; P(n) overwrites S(n)[0, KB/2)
-    static constexpr int TM_O = 2 * S_COLS;
-    static constexpr int TM_COLS = 512;
-    static_assert(SEQ % KB == 0 && KB % 16 == 0 && KB <= 256 && (KB % 64 == 0 || KB % 64 == 16), "key blocking");
-    static_assert(NKB == 1 || NKB % 2 == 1, "the row-sum hand-off buffer relies on the groups swapping roles every tile");
+    static constexpr int OFF_L = OFF_M + AT_QTILE * 4;                 // (row sum, its reference maximum) of the non-final group, per tile parity
+    static constexpr int OFF_BAR = OFF_L + 2 * AT_QTILE * 8;
+    static constexpr int SMEM = OFF_BAR + 256 + 1024;                  // + alignment slack
+    // TMEM columns: S_0 | ... | S_{NBUF-1} | O_0 (| O_1); P(n) overwrites S(n)[0, KB/2)
+    static constexpr int S_COLS = KB;
+    static constexpr int TM_O = NBUF * S_COLS;
+    static constexpr int OBUF = (TMC - TM_O) >= 128 ? 2 : 1;
+    static constexpr int TM_COLS = TMC;                                // 256: two CTAs of the S = 144 variant share an SM
+    static_assert(SEQ % KB == 0 && KB % 16 == 0 && KB <= 256 && (KB % 32 == 0 || KB % 32 == 16), "key blocking");
     static_assert((KB * AT_ROWB) % 1024 == 0, "key blocks must start on a swizzle-atom boundary");
-    static_assert(2 * S_COLS + 128 <= 512, "TMEM budget");
+    static_assert(NBUF >= 1 && NBUF <= 4 && TM_O + 64 * OBUF <= TMC && (TMC == 256 || TMC == 512), "TMEM budget");
     static_assert(SMEM <= 232448, "shared memory budget");
 };
 
-// barrier slots
-// (S_FREE[b]: committed by the tensor core after the P V product that read P out of S buffer b)
-// Every barrier that a producer could complete twice before its consumer has looked (a parity wait cannot tell phase k
-// from phase k + 2) exists once per S buffer / tile parity, so that the producer's next arrival depends on the consumer.
-enum { B_QFULL = 0, B_QFREE = 2, B_SFULL = 4, B_SFREE = 6, B_PREADY = 8, B_OFULL = 10, B_OFREE = 12, B_MREADY = 14,
-       B_LREADY = 15, B_DBG = 16, B_COUNT = 17 };
+// Barrier slots.  S_FREE[k] is committed by the tensor core after the P V product that read P out of S buffer k.  Every
+// barrier that a producer could otherwise complete twice before its consumer has looked (a parity wait cannot tell phase
+// i from phase i + 2) exists once per S buffer / O buffer / query slot, so that the producer's next arrival depends on
+// the consumer having gone through.
+enum { B_QFULL = 0, B_QFREE = 2, B_SFULL = 4, B_SFREE = 8, B_PREADY = 12, B_OFULL = 16, B_OFREE = 18, B_MREADY = 20,
+       B_LREADY = 21, B_DBG = 22, B_COUNT = 23 };
 
-template <int SEQ, int KB, int ROT_PAIRS>
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {       // non-blocking probe (try_wait may suspend)
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+template <int SEQ, int KB, int NBUF, int TMC, int ROT_PAIRS>
+__global__ void __launch_bounds__(AT_THREADS, (TMC == 256 ? 2 : 1))
 attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, const float2* __restrict__ rot, long long* trace) {
-    using C = AttnCfg<SEQ, KB>;
+    using C = AttnCfg<SEQ, KB, NBUF, TMC>;
     // optional phase trace (profiling aid, null in production): [cta][role 0 softmax A / 1 mma / 2 loader / 3 softmax B][64] ns
     int n_stamp = 0;
 #define AT_STAMP(role)                                                                                          \
@@ -211,13 +224,17 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
     const bf16* vbase = kbase + heads * 64;
 
     if (threadIdx.x == 0) {
-        mbar_init(&bars[B_QFULL], AT_LOADER_WARPS * 32); mbar_init(&bars[B_QFULL + 1], AT_LOADER_WARPS * 32);
-        mbar_init(&bars[B_QFREE], 1); mbar_init(&bars[B_QFREE + 1], 1);
-        mbar_init(&bars[B_SFULL], 1); mbar_init(&bars[B_SFULL + 1], 1);
-        mbar_init(&bars[B_SFREE], 1); mbar_init(&bars[B_SFREE + 1], 1);
-        mbar_init(&bars[B_PREADY], AT_GROUP_WARPS * 32); mbar_init(&bars[B_PREADY + 1], AT_GROUP_WARPS * 32);
-        mbar_init(&bars[B_OFULL], 1); mbar_init(&bars[B_OFULL + 1], 1);
-        mbar_init(&bars[B_OFREE], AT_GROUP_WARPS * 32); mbar_init(&bars[B_OFREE + 1], AT_GROUP_WARPS * 32);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars[B_QFULL + i], AT_LOADER_WARPS * 32);
+            mbar_init(&bars[B_QFREE + i], 1);
+            mbar_init(&bars[B_OFULL + i], 1);
+            mbar_init(&bars[B_OFREE + i], AT_GROUP_WARPS * 32);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&bars[B_SFULL + i], 1);
+            mbar_init(&bars[B_SFREE + i], 1);
+            mbar_init(&bars[B_PREADY + i], AT_GROUP_WARPS * 32);
+        }
         mbar_init(&bars[B_MREADY], AT_GROUP_WARPS * 32);
         mbar_init(&bars[B_LREADY], AT_GROUP_WARPS * 32);
         mbar_init(&bars[B_DBG], 1);
@@ -231,16 +248,21 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
     if (threadIdx.x == 0) AT_STAMP(0);             // entry
     pdl_wait();                                    // qkv is the previous kernel's output
 
-    // ---- K and V of the whole head -> shared memory.  Thread i copies chunk (i % 8) of rows i / 8, i / 8 + 44, ...
-    // (352 threads = 44 rows per sweep), so it later rotates exactly the K chunks it copied itself: no barrier
-    // between the copy and the rotation.
-    {
-        constexpr int RS = AT_THREADS / 8, MAXR = (SEQ + RS - 1) / RS;
+    // ---- K and V of the whole head -> shared memory (see stage_rows), by the softmax and MMA warps; the loader warps
+    // stage the first query tile meanwhile
+    constexpr int KV_THREADS = (AT_SOFTMAX_WARPS + 1) * 32;
+    if (warp <= AT_SOFTMAX_WARPS) {
+        constexpr int RS = KV_THREADS / 8, MAXR = (SEQ + RS - 1) / RS;
         stage_rows<ROT_PAIRS, RS, MAXR, (MAXR + 1) / 2>(sK, kbase, sV, vbase, ld, threadIdx.x >> 3, threadIdx.x & 7, SEQ, 0, SEQ, rot);
+        fence_proxy_async_smem();                  // generic-proxy stores -> visible to the tensor core's async proxy
+    } else {
+        const int lt = threadIdx.x - KV_THREADS;
+        constexpr int RS = AT_LOADER_WARPS * 4, MAXR = AT_QTILE / RS;
+        stage_rows<ROT_PAIRS, RS, MAXR, MAXR / 2>(sQ, qbase, nullptr, nullptr, ld, lt >> 3, lt & 7, AT_QTILE, 0, SEQ, rot);
+        fence_proxy_async_smem();                  // (q_full[0] is arrived on after the barrier below has published the mbarriers)
     }
-    fence_proxy_async_smem();                      // generic-proxy stores -> visible to the tensor core's async proxy
     tcgen05_fence_before();
-    __syncthreads();
+    __syncthreads();                               // (the loaders arrive at once; mbarriers / TMEM address are published here)
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) AT_STAMP(0);             // K / V staged
@@ -255,33 +277,97 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
         const float sl2 = 0.125f * 1.4426950408889634f;                  // 1/sqrt(64) * log2(e)
         const int ldo = heads * 64;
         float l = 0.f, m_mine = -INFINITY;                               // this thread's share of the row sum, relative to m_mine
+        // epilogue of tile t: O / (row sum) -> bf16 -> out[row][head*64 ..]; l_fin / m_fin: this thread's share of the row sum
+        auto epilogue = [&](int t, float l_fin, float m_fin) {
+            float lt = l_fin;
+            if (C::NKB > 1) {
+                mbar_wait(&bars[B_LREADY], t & 1);
+                const float2 o = sL[(t & 1) * AT_QTILE + row];
+                lt += o.x * ex2_approx((o.y - m_fin) * sl2);
+            }
+            const float inv = 1.0f / lt;
+            const uint32_t ob = t % C::OBUF;
+            mbar_wait(&bars[B_OFULL + ob], (t / C::OBUF) & 1);
+            tcgen05_fence_after();
+            if (tr) AT_STAMP(tr_role);                                   // O full
+            const int grow = t * AT_QTILE + row;
+            bf16* dst = out + (row_base + grow) * ldo + head * 64;
+            uint32_t o0[32], o1[32];
+            tmem_ld_32x32(tlane + C::TM_O + ob * 64, o0);
+            tmem_ld_32x32(tlane + C::TM_O + ob * 64 + 32, o1);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            mbar_arrive(&bars[B_OFREE + ob]);                            // O is in registers: a later tile may overwrite it
+            if (grow < SEQ) {
+#pragma unroll
+                for (int c = 0; c < 32; c += 8) {
+                    uint4 w;
+                    w.x = pack_bf16x2(__uint_as_float(o0[c]) * inv, __uint_as_float(o0[c + 1]) * inv);
+                    w.y = pack_bf16x2(__uint_as_float(o0[c + 2]) * inv, __uint_as_float(o0[c + 3]) * inv);
+                    w.z = pack_bf16x2(__uint_as_float(o0[c + 4]) * inv, __uint_as_float(o0[c + 5]) * inv);
+                    w.w = pack_bf16x2(__uint_as_float(o0[c + 6]) * inv, __uint_as_float(o0[c + 7]) * inv);
+                    *reinterpret_cast<uint4*>(dst + c) = w;
+                }
+#pragma unroll
+                for (int c = 0; c < 32; c += 8) {
+                    uint4 w;
+                    w.x = pack_bf16x2(__uint_as_float(o1[c]) * inv, __uint_as_float(o1[c + 1]) * inv);
+                    w.y = pack_bf16x2(__uint_as_float(o1[c + 2]) * inv, __uint_as_float(o1[c + 3]) * inv);
+                    w.z = pack_bf16x2(__uint_as_float(o1[c + 4]) * inv, __uint_as_float(o1[c + 5]) * inv);
+                    w.w = pack_bf16x2(__uint_as_float(o1[c + 6]) * inv, __uint_as_float(o1[c + 7]) * inv);
+                    *reinterpret_cast<uint4*>(dst + 32 + c) = w;
+                }
+            }
+            if (tr) AT_STAMP(tr_role);                                   // tile stored
+        };
+        int pend_t = -1;
+        float pend_l = 0.f, pend_m = 0.f;
 #pragma unroll 1
         for (int n = grp; n < C::NBLK; n += 2) {
             const int t = n / C::NKB, j = n - t * C::NKB;
-            const uint32_t b = n & 1;                                    // == grp: this group always reads S buffer `grp`
-            mbar_wait(&bars[B_SFULL + b], (n >> 1) & 1);
+            const uint32_t k = n % NBUF, u = n / NBUF;                   // S buffer and how often it has been used before
+            // A parity wait only tells the current phase from the previous one.  With an odd number of S buffers the
+            // previous use of buffer k belonged to the OTHER group, so this group has not seen that phase complete: go
+            // through it first (it normally has completed long ago), or a wait for phase u posted while the barrier is
+            // still in phase u - 1 returns at once (NBUF = 1: group 1 polls S_FULL[0] from the start of the kernel).
+            if ((NBUF & 1) && u > 0) mbar_wait(&bars[B_SFULL + k], (u - 1) & 1);
+            mbar_wait(&bars[B_SFULL + k], u & 1);
             tcgen05_fence_after();
             if (tr) AT_STAMP(tr_role);                                   // S full
-            const uint32_t ta = tlane + b * C::S_COLS;
-            constexpr int FULL = KB / 64 * 64;                           // columns swept 64 at a time; 16-column tail (KB = 144)
-            // ---- row maximum of this block (first sweep over the S tile)
-            float bm = -INFINITY;
+            const uint32_t ta = tlane + k * C::S_COLS;
+            constexpr int FULL = KB / 32 * 32;                           // columns swept 32 at a time; 16-column tail (KB = 144)
+            constexpr int NCH = FULL / 32;
+            // ---- row maximum of this block (first sweep over the S tile; the next chunk's load is in flight while one is reduced)
+            float bm0 = -INFINITY, bm1 = -INFINITY;
+            {
+                uint32_t va[32], vb[32];
+                tmem_ld_32x32(ta, va);
 #pragma unroll
-            for (int c = 0; c < FULL; c += 64) {
-                uint32_t v0[32], v1[32];
-                tmem_ld_32x32(ta + c, v0);
-                tmem_ld_32x32(ta + c + 32, v1);
-                tmem_ld_wait();
+                for (int ch = 0; ch < NCH; ++ch) {
+                    tmem_ld_wait();
+                    if (ch + 1 < NCH) {
+                        if (ch & 1) tmem_ld_32x32(ta + (ch + 1) * 32, va);
+                        else tmem_ld_32x32(ta + (ch + 1) * 32, vb);
+                    }
+                    const uint32_t(&v)[32] = (ch & 1) ? vb : va;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) bm = fmaxf(bm, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+                    for (int i = 0; i < 32; i += 2) {
+                        bm0 = fmaxf(bm0, __uint_as_float(v[i]));
+                        bm1 = fmaxf(bm1, __uint_as_float(v[i + 1]));
+                    }
+                }
+                if (FULL < KB) {
+                    uint32_t v[16];
+                    tmem_ld_32x16(ta + FULL, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        bm0 = fmaxf(bm0, __uint_as_float(v[i]));
+                        bm1 = fmaxf(bm1, __uint_as_float(v[i + 1]));
+                    }
+                }
             }
-            if (FULL < KB) {
-                uint32_t v[16];
-                tmem_ld_32x16(ta + FULL, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) bm = fmaxf(bm, __uint_as_float(v[i]));
-            }
+            const float bm = fmaxf(bm0, bm1);
             // ---- the maximum this row is expressed in: the previous block's, unless this block's exceeds it by > 2^8
             float m_use = bm, o_scale = 1.0f;
             if (n > 0) mbar_wait(&bars[B_MREADY], (n - 1) & 1);          // (every block waits: keeps the phases in step)
@@ -302,11 +388,11 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
             }
             if (j > 0 && __any_sync(0xffffffffu, o_scale != 1.0f)) {
                 // rare: this block raised the row maximum by more than 2^8 - rescale the row's partial output once the
-                // previous P V product has completed (its commit on S_FREE of the other buffer), before the next one
+                // previous P V product has completed (its commit on the S_FREE of its buffer), before the next one
                 // accumulates onto it
-                mbar_wait(&bars[B_SFREE + (b ^ 1)], ((n - 1) >> 1) & 1);
+                mbar_wait(&bars[B_SFREE + (n - 1) % NBUF], ((n - 1) / NBUF) & 1);
                 tcgen05_fence_after();
-                const uint32_t to = tlane + C::TM_O + (t & 1) * 64;
+                const uint32_t to = tlane + C::TM_O + (t % C::OBUF) * 64;
 #pragma unroll
                 for (int c = 0; c < 64; c += 32) {
                     uint32_t o[32];
@@ -317,82 +403,73 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
                     tmem_st_32x32(to + c, o);
                 }
             }
-            // ---- exponentials (second sweep): 32 S columns in, 16 P columns (bf16 pairs) out, over the columns just read
+            // ---- exponentials (second sweep): 32 S columns in, 16 P columns (bf16 pairs) out over the columns just read; the
+            // next chunk's load is issued before the current one is exponentiated
             const float mo = m_use * sl2;
+            float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;                // independent partial sums (no serial FADD chain)
+            {
+                uint32_t va[32], vb[32];
+                tmem_ld_32x32(ta, va);
 #pragma unroll
-            for (int c = 0; c < FULL; c += 32) {
-                uint32_t v[32], pk[16];
-                tmem_ld_32x32(ta + c, v);
-                tmem_ld_wait();
+                for (int ch = 0; ch < NCH; ++ch) {
+                    tmem_ld_wait();
+                    if (ch + 1 < NCH) {
+                        if (ch & 1) tmem_ld_32x32(ta + (ch + 1) * 32, va);
+                        else tmem_ld_32x32(ta + (ch + 1) * 32, vb);
+                    } else if (FULL < KB) {
+                        // (tail handled below with its own load)
+                    }
+                    const uint32_t(&v)[32] = (ch & 1) ? vb : va;
+                    uint32_t pk[16];
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float p0 = ex2_approx(__uint_as_float(v[i]) * sl2 - mo), p1 = ex2_approx(__uint_as_float(v[i + 1]) * sl2 - mo);
-                    l += p0 + p1;                                        // fp32 sum of the unrounded probabilities
-                    pk[i / 2] = pack_bf16x2(p0, p1);
+                    for (int i = 0; i < 32; i += 4) {
+                        const float p0 = ex2_approx(__uint_as_float(v[i]) * sl2 - mo), p1 = ex2_approx(__uint_as_float(v[i + 1]) * sl2 - mo);
+                        const float p2 = ex2_approx(__uint_as_float(v[i + 2]) * sl2 - mo), p3 = ex2_approx(__uint_as_float(v[i + 3]) * sl2 - mo);
+                        l0 += p0; l1 += p1; l2 += p2; l3 += p3;          // fp32 sum of the unrounded probabilities
+                        pk[i / 2] = pack_bf16x2(p0, p1);
+                        pk[i / 2 + 1] = pack_bf16x2(p2, p3);
+                    }
+                    tmem_st_32x16(ta + ch * 16, pk);
                 }
-                tmem_st_32x16(ta + c / 2, pk);
-            }
-            if (FULL < KB) {
-                uint32_t v[16], pk[8];
-                tmem_ld_32x16(ta + FULL, v);
-                tmem_ld_wait();
+                if (FULL < KB) {
+                    uint32_t v[16], pk[8];
+                    tmem_ld_32x16(ta + FULL, v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; i += 2) {
-                    const float p0 = ex2_approx(__uint_as_float(v[i]) * sl2 - mo), p1 = ex2_approx(__uint_as_float(v[i + 1]) * sl2 - mo);
-                    l += p0 + p1;
-                    pk[i / 2] = pack_bf16x2(p0, p1);
+                    for (int i = 0; i < 16; i += 4) {
+                        const float p0 = ex2_approx(__uint_as_float(v[i]) * sl2 - mo), p1 = ex2_approx(__uint_as_float(v[i + 1]) * sl2 - mo);
+                        const float p2 = ex2_approx(__uint_as_float(v[i + 2]) * sl2 - mo), p3 = ex2_approx(__uint_as_float(v[i + 3]) * sl2 - mo);
+                        l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+                        pk[i / 2] = pack_bf16x2(p0, p1);
+                        pk[i / 2 + 1] = pack_bf16x2(p2, p3);
+                    }
+                    tmem_st_32x8(ta + FULL / 2, pk);
                 }
-                tmem_st_32x8(ta + FULL / 2, pk);
             }
+            l += (l0 + l1) + (l2 + l3);
             tmem_st_wait();
             tcgen05_fence_before();
-            mbar_arrive(&bars[B_PREADY + b]);                            // P(n) is in tensor memory
+            mbar_arrive(&bars[B_PREADY + k]);                            // P(n) is in tensor memory
             if (tr) AT_STAMP(tr_role);                                   // P written
             // ---- end of this group's work on the tile
+            if (pend_t >= 0) {                                           // the tile this group finished one block ago: its O is complete by now
+                // (before the hand-off below: L_READY must not complete its next phase while a thread of this group still
+                // waits for the previous one - a parity wait cannot tell them apart)
+                epilogue(pend_t, pend_l, pend_m);
+                pend_t = -1;
+            }
             if (C::NKB > 1 && j == C::NKB - 2) {                         // the OTHER group finishes the tile: hand it our share
-                sL[row] = make_float2(l, m_mine);
+                sL[(t & 1) * AT_QTILE + row] = make_float2(l, m_mine);
                 mbar_arrive(&bars[B_LREADY]);
             }
             if (j == C::NKB - 1) {
-                // epilogue of tile t: O / (row sum) -> bf16 -> out[row][head*64 ..]
-                float lt = l;
-                if (C::NKB > 1) {
-                    mbar_wait(&bars[B_LREADY], t & 1);
-                    const float2 o = sL[row];
-                    lt += o.x * ex2_approx((o.y - m_mine) * sl2);
-                }
-                const float inv = 1.0f / lt;
-                const uint32_t ob = t & 1;
-                mbar_wait(&bars[B_OFULL + ob], (t >> 1) & 1);
-                tcgen05_fence_after();
-                if (tr) AT_STAMP(tr_role);                               // O full
-                const int grow = t * AT_QTILE + row;
-                bf16* dst = out + (row_base + grow) * ldo + head * 64;
-#pragma unroll
-                for (int c0 = 0; c0 < 64; c0 += 32) {
-                    uint32_t o[32];
-                    tmem_ld_32x32(tlane + C::TM_O + ob * 64 + c0, o);
-                    tmem_ld_wait();
-                    if (c0 == 32) {
-                        tcgen05_fence_before();
-                        mbar_arrive(&bars[B_OFREE + ob]);
-                    }
-                    if (grow < SEQ) {
-#pragma unroll
-                        for (int c = 0; c < 32; c += 8) {
-                            uint4 w;
-                            w.x = pack_bf16x2(__uint_as_float(o[c]) * inv, __uint_as_float(o[c + 1]) * inv);
-                            w.y = pack_bf16x2(__uint_as_float(o[c + 2]) * inv, __uint_as_float(o[c + 3]) * inv);
-                            w.z = pack_bf16x2(__uint_as_float(o[c + 4]) * inv, __uint_as_float(o[c + 5]) * inv);
-                            w.w = pack_bf16x2(__uint_as_float(o[c + 6]) * inv, __uint_as_float(o[c + 7]) * inv);
-                            *reinterpret_cast<uint4*>(dst + c0 + c) = w;
-                        }
-                    }
-                }
-                if (tr) AT_STAMP(tr_role);                               // tile stored
+                // This group owns the epilogue of tile t.  With two O buffers it is deferred until after the group's next
+                // block: waiting here for the last P V product would hold up the other group through the row-maximum chain.
+                if (C::OBUF == 2 && n + 2 < C::NBLK) { pend_t = t; pend_l = l; pend_m = m_mine; }
+                else epilogue(t, l, m_mine);
             }
         }
-    } else if (warp == AT_SOFTMAX_WARPS) {
+        } else if (warp == AT_SOFTMAX_WARPS) {
         // =========================================================================== MMA issuer (one thread)
         if (lane == 0) {
             constexpr uint32_t idesc_s = umma_idesc_bf16(AT_QTILE, KB);              // S = Q K^T: both operands K-major
@@ -404,12 +481,13 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
             const uint64_t desc_v0 = umma_desc_sw128(smem_u32(sV));
             auto try_pv = [&](int n) -> bool {                   // O += P(n) V: needs P written (and, first block of a tile, O read out)
                 const int t = n / C::NKB, j = n - t * C::NKB;
-                if (j == 0 && t >= 2 && !mbar_try_wait(&bars[B_OFREE + (t & 1)], ((t >> 1) - 1) & 1)) return false;
-                if (!mbar_try_wait(&bars[B_PREADY + (n & 1)], (n >> 1) & 1)) return false;
+                const uint32_t k = n % NBUF, ob = t % C::OBUF;
+                if (j == 0 && t >= C::OBUF && !mbar_test(&bars[B_OFREE + ob], (t / C::OBUF - 1) & 1)) return false;
+                if (!mbar_test(&bars[B_PREADY + k], (n / NBUF) & 1)) return false;
                 tcgen05_fence_after();
                 AT_STAMP(1);                       // P ready
-                const uint32_t d = tmem_base + C::TM_O + (t & 1) * 64;
-                const uint32_t pa = tmem_base + (n & 1) * C::S_COLS;         // P(n): 8 columns per K step of 16 keys
+                const uint32_t d = tmem_base + C::TM_O + ob * 64;
+                const uint32_t pa = tmem_base + k * C::S_COLS;                   // P(n): 8 columns per K step of 16 keys
                 // B descriptors = a base built once + compile-time offsets (16-byte units): the issuing thread's own scalar
                 // code is what bounds a short MMA (scripts/probe_umma_pv.cu: ~100 cycles per MMA with the descriptor
                 // rebuilt in the loop, ~61 with it precomputed)
@@ -417,34 +495,35 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
 #pragma unroll
                 for (int ks = 0; ks < PV_STEPS; ++ks)
                     umma_bf16_ts(d, pa + ks * 8, db0 + ks * (16 * AT_ROWB / 16), idesc_o, (j | ks) != 0 ? 1u : 0u);
-                umma_commit(&bars[B_SFREE + (n & 1)]);                       // S buffer (and the P inside it) consumed
-                if (j == C::NKB - 1) umma_commit(&bars[B_OFULL + (t & 1)]);
-                if (trace != nullptr && dbg_pv) {  // profiling only (GTAV_ATTN_TRACE bit 0 of the address set): time the product itself
+                umma_commit(&bars[B_SFREE + k]);                                 // S buffer (and the P inside it) consumed
+                if (j == C::NKB - 1) umma_commit(&bars[B_OFULL + ob]);
+                if (trace != nullptr && dbg_pv) {  // profiling only: time the product itself
                     umma_commit(&bars[B_DBG]);
                     mbar_wait(&bars[B_DBG], n_dbg++ & 1);
                     AT_STAMP(1);                   // P V done
                 }
                 return true;
             };
-            auto try_s = [&](int n) -> bool {                    // S(n) = Q K^T: needs the query tile staged and the S buffer read out
+            auto try_s = [&](int n) -> bool {                    // S(n) = Q K^T: needs the query tile staged and the S buffer consumed
                 const int t = n / C::NKB, j = n - t * C::NKB;
-                const uint32_t b = n & 1;
-                if (j == 0 && !mbar_try_wait(&bars[B_QFULL + (t & 1)], (t >> 1) & 1)) return false;
-                if (n >= 2 && !mbar_try_wait(&bars[B_SFREE + b], ((n >> 1) - 1) & 1)) return false;
+                const uint32_t k = n % NBUF;
+                if (j == 0 && !mbar_test(&bars[B_QFULL + (t & 1)], (t >> 1) & 1)) return false;
+                if (n >= NBUF && !mbar_test(&bars[B_SFREE + k], (n / NBUF - 1) & 1)) return false;
                 tcgen05_fence_after();
-                const uint32_t d = tmem_base + b * C::S_COLS;
+                const uint32_t d = tmem_base + k * C::S_COLS;
                 const uint64_t da0 = desc_q0 + static_cast<uint64_t>((t & 1) * (C::Q_BYTES / 16));
                 const uint64_t db0 = desc_k0 + static_cast<uint64_t>(j * (KB * AT_ROWB / 16));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16_ss(d, da0 + 2 * k, db0 + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-                umma_commit(&bars[B_SFULL + b]);
+                for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(d, da0 + 2 * kk, db0 + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
+                umma_commit(&bars[B_SFULL + k]);
                 if (j == C::NKB - 1) umma_commit(&bars[B_QFREE + (t & 1)]);          // last read of this query tile
                 AT_STAMP(1);                       // S(n) issued
                 return true;
             };
-            // Whichever of the two next products has its operands ready is issued, S first: the S tile of block n + 1 (and
-            // n + 2 as soon as its buffer has been read out) must not queue behind a P V product that is still waiting for
-            // its probabilities - the softmax group that owns the buffer would sit idle for that long.
+            // Whichever of the two next products has its operands ready is issued, S first: an S tile must not queue behind
+            // a P V product that is still waiting for its probabilities - the softmax group that owns the buffer would sit
+            // idle for that long.  Non-blocking probes (mbarrier.test_wait): try_wait may suspend the thread for a
+            // microsecond while the OTHER product became ready.
             int next_s = 0, next_pv = 0;
             uint32_t idle = 0;
             while (next_pv < C::NBLK) {
@@ -452,7 +531,7 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
                 if (next_s < C::NBLK && try_s(next_s)) { ++next_s; did = true; }
                 else if (next_pv < next_s && try_pv(next_pv)) { ++next_pv; did = true; }
                 if (did) idle = 0;
-                else if (++idle > (1u << 24)) { printf("gtav: attention MMA scheduler stalled (block %d)\n", blockIdx.x); __trap(); }
+                else if (++idle > (1u << 26)) { printf("gtav: attention MMA scheduler stalled (block %d)\n", blockIdx.x); __trap(); }
             }
         }
     } else {
@@ -463,10 +542,12 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
         for (int t = 0; t < C::QTILES; ++t) {
             if (t >= 2) mbar_wait(&bars[B_QFREE + (t & 1)], ((t >> 1) - 1) & 1);
             if (lt == 0) AT_STAMP(2);              // slot free
-            uint8_t* dstq = sQ + (t & 1) * C::Q_BYTES;
-            constexpr int RS = AT_LOADER_WARPS * 4, MAXR = AT_QTILE / RS;
-            stage_rows<ROT_PAIRS, RS, MAXR, MAXR / 2>(dstq, qbase, nullptr, nullptr, ld, lt >> 3, c, AT_QTILE, t * AT_QTILE, SEQ, rot);
-            fence_proxy_async_smem();
+            if (t > 0) {                           // (tile 0 was staged next to the K / V staging, before the set-up barrier)
+                uint8_t* dstq = sQ + (t & 1) * C::Q_BYTES;
+                constexpr int RS = AT_LOADER_WARPS * 4, MAXR = AT_QTILE / RS;
+                stage_rows<ROT_PAIRS, RS, MAXR, MAXR / 2>(dstq, qbase, nullptr, nullptr, ld, lt >> 3, c, AT_QTILE, t * AT_QTILE, SEQ, rot);
+                fence_proxy_async_smem();
+            }
             mbar_arrive(&bars[B_QFULL + (t & 1)]);
             if (lt == 0) AT_STAMP(2);              // staged
         }
@@ -482,11 +563,11 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
 #undef AT_STAMP
 }
 
-template <int SEQ, int KB, int ROT_PAIRS>
+template <int SEQ, int KB, int NBUF, int TMC, int ROT_PAIRS>
 int launch_tc(const bf16* qkv, bf16* out, int groups, int heads, const float2* rot, cudaStream_t s) {
-    using C = AttnCfg<SEQ, KB>;
+    using C = AttnCfg<SEQ, KB, NBUF, TMC>;
     static bool configured = false;
-    auto kern = attn_tc_kernel<SEQ, KB, ROT_PAIRS>;
+    auto kern = attn_tc_kernel<SEQ, KB, NBUF, TMC, ROT_PAIRS>;
     if (!configured) {
         GTAV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         configured = true;
@@ -503,8 +584,16 @@ int launch_tc(const bf16* qkv, bf16* out, int groups, int heads, const float2* r
 int launch_attention_tc(const bf16* qkv, bf16* out, int groups, int seq, int heads, const float2* rot, int rot_pairs,
                         cudaStream_t s) {
     if (groups <= 0) return 0;
-    if (seq == 576 && rot_pairs == 16) return launch_tc<576, 192, 16>(qkv, out, groups, heads, rot, s);
-    if (seq == 144 && rot_pairs == 32) return launch_tc<144, 144, 32>(qkv, out, groups, heads, rot, s);
+    if (seq == 576 && rot_pairs == 16) {
+        // GTAV_ATTN_KB=96 (A/B measurements): 6 key blocks per tile in 4 S buffers instead of 3 blocks of 192 keys in 2
+        // (measured 146 us against 128 us for 32 frames: the per-block hand-offs cost more than the extra buffers save)
+        const char* e = getenv("GTAV_ATTN_KB");
+        if (e != nullptr && atoi(e) == 96) return launch_tc<576, 96, 4, 512, 16>(qkv, out, groups, heads, rot, s);
+        return launch_tc<576, 192, 2, 512, 16>(qkv, out, groups, heads, rot, s);
+    }
+    // S = 144: one S buffer and one O buffer in 256 TMEM columns, 72 KB of shared memory -> two CTAs per SM hide each other's
+    // staging and hand-off latencies (one CTA has only two (tile, block) steps to pipeline)
+    if (seq == 144 && rot_pairs == 32) return launch_tc<144, 144, 1, 256, 32>(qkv, out, groups, heads, rot, s);
     set_error("attention (tcgen05): unsupported (seq=%d, rot_pairs=%d); built for (144,32) and (576,16)", seq, rot_pairs);
     return -1;
 }
