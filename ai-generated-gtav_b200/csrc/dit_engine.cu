@@ -146,10 +146,11 @@ int build_shape(gtav_dit_plan_s* p, Shape* sh, int frames, bool allow_skinny) {
         GemmParams p1 = gp(p->mlp, 4 * D, hw.fc1_b, M, 4 * D, D);
         GemmParams p2 = gp(p->h, D, hw.fc2_b, M, D, 4 * D);
         p2.res = p->h; p2.ldr = D; p2.gate = modl + 5 * D; p2.gate_ld = W; p2.rows_per_frame = S;
-        // each tiled GEMM pulls the next one's weights into L2 while it runs (weights: 2 bytes per element).  Not the
-        // weight-streaming kernel: it requests its own weight slab first thing, before the dependency wait, and the
-        // extra L2 fills then only compete with the operand loads (bench_graph.py --engine: 1.208 ms per step with the
-        // prefetch, 1.191 ms without; tiled passes: 2.312 with, 2.331 without).  GTAV_PREFETCH=0 / 1 forces off / on.
+        // Each tiled GEMM pulls the next one's weights into L2 while it runs (weights: 2 bytes per element).  Not the
+        // weight-streaming kernel: measured in the real step (scripts/bench_graph.py --engine), a prefetch issued at its
+        // start competes with its own slab loads (1.208 vs 1.191 ms per step, round 1), and one issued after its MMAs -
+        // when HBM is idle - still costs 2 % (1.191 vs 1.169 ms, round 2): the next launch's slab request is not what its
+        // critical path waits for.  GTAV_PREFETCH=0 / 1 forces off / on everywhere.
         const size_t DD = static_cast<size_t>(D) * D * 2;
         const char* pfenv = getenv("GTAV_PREFETCH");
         const bool pf_off = pfenv != nullptr && pfenv[0] == '0', pf_force = pfenv != nullptr && pfenv[0] == '1';

@@ -409,8 +409,6 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     const uint32_t tmem_base = gemm_cta ? *tmem_slot : 0u;
     pdl_trigger();
     if (!gemm_cta && threadIdx.x == 128) SK_STAMP(1);                          // set-up done
-    if (warp >= 4)     // idle until the accumulator is ready: pull the NEXT GEMM's weights into L2 meanwhile
-        l2_prefetch_share(p.g.prefetch, p.g.prefetch_bytes, (blockIdx.x * 4 + (warp - 4)) * 32 + lane, gridDim.x * 128);
     if (gemm_cta && warp == 2) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(128, SK_NT);
@@ -481,6 +479,11 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         mbar_wait(bar_acc, 0);
         tcgen05_fence_after();
         if (threadIdx.x == 128) SK_STAMP(4);                                   // accumulator complete
+        // This CTA's operand slab has been consumed and HBM is idle for the rest of the launch (partials, rendezvous and
+        // reduce only move data through L2): pull the NEXT GEMM's weights into L2 now, so that its slab request - issued
+        // when its CTAs start, ~5 us from here - is an L2 hit instead of an HBM round trip at the head of its critical
+        // path.  (Issued at kernel start, round 1, the prefetch competed with this launch's own slab loads and cost 1.5 %.)
+        l2_prefetch_share(p.g.prefetch, p.g.prefetch_bytes, blockIdx.x * SK_THREADS + threadIdx.x, p.gemm_ctas * SK_THREADS);
         const int c0 = warp < 4 ? half : 0;
         const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0;
         float* mine = p.ws + static_cast<size_t>(blockIdx.x) * total * 128 + static_cast<size_t>(c0) * 128 + row;

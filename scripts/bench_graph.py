@@ -123,8 +123,9 @@ def engine_steps():
     t = torch.tensor([[15, 15, 15, 15, 500]], device=dev)
     rows = torch.arange(5, dtype=torch.int32, device=dev)
     out = torch.empty((1, 1, 16, 18, 32), dtype=torch.bfloat16, device=dev)
-    for label, env in (("default (weight-streaming GEMM, L2 prefetch, LN + temporal attention in the reduce)", {}),
-                       ("separate LN / temporal-attention kernels", {"GTAV_FUSE": "0"}), ("L2 prefetch of the next weights also in the weight-streaming GEMM", {"GTAV_PREFETCH": "1"}),
+    for label, env in (("default (weight-streaming GEMM, LN + temporal attention in the reduce)", {}),
+                       ("next weights prefetched into L2 after the weight-streaming GEMM's MMAs", {"GTAV_PREFETCH": "1"}),
+                       ("separate LN / temporal-attention kernels", {"GTAV_FUSE": "0"}),
                        ("to_out with 16 K-splits", {"GTAV_SK_SPLITS": "0,16,0,0"}),
                        ("tiled GEMM everywhere", {"GTAV_SKINNY": "0"}),
                        ("no PDL", {"GTAV_PDL_OFF_NOTE": "set GTAV_PDL=0 before start to test"})):

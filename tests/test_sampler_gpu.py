@@ -136,7 +136,8 @@ def test_sampler_without_actions_and_growing_window(models):
 
 def test_frame_stream_equals_batch_generate(models):
     """Interactive frame-at-a-time generation (per-frame action, single-frame decode) == Sampler.generate on the same
-    noise draws and the same action sequence: latents bit for bit, decoded frames identical."""
+    noise draws and the same action sequence: latents bit for bit, decoded frames equal up to the rounding difference of the two
+    attention kernels the VAE uses at different frame counts (<= 4 LSB, mean < 0.5 LSB: bf16 carries 8 bits at pixel scale)."""
     from gtav_b200.sampler import Sampler
     dit, vae = models
     steps, total, n_prompt, B = 3, 8, 2, 2
@@ -153,7 +154,12 @@ def test_frame_stream_equals_batch_generate(models):
         f, z = st.next(action=acts[:, i], noise=noise[:, i - n_prompt])
         assert torch.equal(z, lat[:, i]), f"frame {i}: streamed latent differs from the batch rollout"
         assert f.shape == (B, 360, 640, 3) and f.dtype == torch.uint8
-        assert torch.equal(f, frames[:, i]), f"frame {i}: streamed pixels differ"
+        # same latent, but a 2-frame decode runs the mma.sync attention and the 16-frame decode the tcgen05 one (attn_mma.cu:
+        # selection by size): the two round differently inside bf16, so pixels may differ by an LSB or two
+        d = (f.int() - frames[:, i].int()).abs()
+        if i == n_prompt:
+            print(f"streamed vs batch-decoded pixels: max {int(d.max())} LSB, mean {float(d.float().mean()):.4f} LSB")
+        assert int(d.max()) <= 4 and float(d.float().mean()) < 0.5, f"frame {i}: streamed pixels differ (max {int(d.max())}, mean {float(d.float().mean()):.4f})"
     assert st.frames_generated == total - n_prompt
     with pytest.raises(RuntimeError, match="action"):
         st.next()                                                   # opened with actions: every frame needs one
