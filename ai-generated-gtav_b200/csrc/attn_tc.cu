@@ -37,10 +37,11 @@ namespace gtav {
 
 namespace {
 
-constexpr int AT_GROUP_WARPS = 4;                     // one softmax warpgroup = 128 query rows
-constexpr int AT_SOFTMAX_WARPS = 2 * AT_GROUP_WARPS;
+constexpr int AT_GROUP_WARPS = 4;                     // one softmax warpgroup = 128 query rows (one warp per TMEM lane quadrant)
 constexpr int AT_LOADER_WARPS = 2;
-constexpr int AT_THREADS = (AT_SOFTMAX_WARPS + 1 + AT_LOADER_WARPS) * 32;      // 352
+constexpr int AT_MMA_WARPS = 1;                       // one thread issues every MMA (two issuing threads, one per product, were
+                                                      // measured: 134 vs 127 us for 32 frames, and no gain from either ordering)
+__host__ __device__ constexpr int at_threads(int groups) { return (groups * AT_GROUP_WARPS + AT_MMA_WARPS + AT_LOADER_WARPS) * 32; }   // 352 (2 groups)
 constexpr int AT_QTILE = 128;
 constexpr int AT_ROWB = 128;                          // bytes per staged row (64 bf16)
 constexpr float AT_LAZY = 8.0f;                       // rescale only when the maximum grows by more than 2^8
@@ -146,7 +147,7 @@ __device__ __forceinline__ void stage_rows(uint8_t* img, const bf16* src, uint8_
 // kind::f16 instruction descriptor with an MN-major B operand (bit 16): V staged as [key][64 dims]
 __host__ __device__ constexpr uint32_t idesc_bf16_bmn(int m, int n) { return umma_idesc_bf16(m, n) | (1u << 16); }
 
-template <int SEQ, int KB, int NBUF, int TMC>
+template <int SEQ, int KB, int NBUF, int TMC, int G>
 struct AttnCfg {
     static constexpr int NKB = SEQ / KB;                               // key blocks per query tile
     static constexpr int QTILES = (SEQ + AT_QTILE - 1) / AT_QTILE;
@@ -156,8 +157,9 @@ struct AttnCfg {
     static constexpr int OFF_V = KV_BYTES;
     static constexpr int OFF_Q = 2 * KV_BYTES;
     static constexpr int OFF_M = OFF_Q + 2 * Q_BYTES;                  // running row maximum handed from block to block
-    static constexpr int OFF_L = OFF_M + AT_QTILE * 4;                 // (row sum, its reference maximum) of the non-final group, per tile parity
-    static constexpr int OFF_BAR = OFF_L + 2 * AT_QTILE * 8;
+    static constexpr int OFF_L = OFF_M + AT_QTILE * 4;                 // (row sum, its reference maximum) of each group, per tile parity
+    static constexpr int OFF_BAR = OFF_L + 2 * G * AT_QTILE * 8;
+    static constexpr int L_PUBLISHERS = (NKB < G ? NKB : G) - 1;       // groups other than the one that finishes a tile
     static constexpr int SMEM = OFF_BAR + 256 + 1024;                  // + alignment slack
     // TMEM columns: S_0 | ... | S_{NBUF-1} | O_0 (| O_1); P(n) overwrites S(n)[0, KB/2)
     static constexpr int S_COLS = KB;
@@ -189,10 +191,12 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {     
     return ok != 0;
 }
 
-template <int SEQ, int KB, int NBUF, int TMC, int ROT_PAIRS>
-__global__ void __launch_bounds__(AT_THREADS, (TMC == 256 ? 2 : 1))
+template <int SEQ, int KB, int NBUF, int TMC, int G, int ROT_PAIRS>
+__global__ void __launch_bounds__(at_threads(G), (TMC == 256 ? 2 : 1))
 attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, const float2* __restrict__ rot, long long* trace) {
-    using C = AttnCfg<SEQ, KB, NBUF, TMC>;
+    using C = AttnCfg<SEQ, KB, NBUF, TMC, G>;
+    constexpr int AT_SOFTMAX_WARPS = G * AT_GROUP_WARPS;
+    constexpr int AT_THREADS = at_threads(G);
     // optional phase trace (profiling aid, null in production): [cta][role 0 softmax A / 1 mma / 2 loader / 3 softmax B][64] ns
     int n_stamp = 0;
 #define AT_STAMP(role)                                                                                          \
@@ -200,7 +204,7 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
         if (trace != nullptr && n_stamp < 64) {                                                                 \
             long long t__;                                                                                      \
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                                            \
-            trace[(static_cast<size_t>(blockIdx.x) * 4 + (role)) * 64 + n_stamp++] = t__;                       \
+            reinterpret_cast<long long*>(reinterpret_cast<uintptr_t>(trace) & ~uintptr_t(15))[(static_cast<size_t>(blockIdx.x) * 4 + (role)) * 64 + n_stamp++] = t__; \
         }                                                                                                       \
     } while (0)
     extern __shared__ uint8_t smem_raw[];
@@ -236,7 +240,7 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
             mbar_init(&bars[B_PREADY + i], AT_GROUP_WARPS * 32);
         }
         mbar_init(&bars[B_MREADY], AT_GROUP_WARPS * 32);
-        mbar_init(&bars[B_LREADY], AT_GROUP_WARPS * 32);
+        mbar_init(&bars[B_LREADY], (C::L_PUBLISHERS > 0 ? C::L_PUBLISHERS : 1) * AT_GROUP_WARPS * 32);
         mbar_init(&bars[B_DBG], 1);
         fence_barrier_init();
     }
@@ -250,8 +254,8 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
 
     // ---- K and V of the whole head -> shared memory (see stage_rows), by the softmax and MMA warps; the loader warps
     // stage the first query tile meanwhile
-    constexpr int KV_THREADS = (AT_SOFTMAX_WARPS + 1) * 32;
-    if (warp <= AT_SOFTMAX_WARPS) {
+    constexpr int KV_THREADS = (AT_SOFTMAX_WARPS + AT_MMA_WARPS) * 32;
+    if (warp < AT_SOFTMAX_WARPS + AT_MMA_WARPS) {
         constexpr int RS = KV_THREADS / 8, MAXR = (SEQ + RS - 1) / RS;
         stage_rows<ROT_PAIRS, RS, MAXR, (MAXR + 1) / 2>(sK, kbase, sV, vbase, ld, threadIdx.x >> 3, threadIdx.x & 7, SEQ, 0, SEQ, rot);
         fence_proxy_async_smem();                  // generic-proxy stores -> visible to the tensor core's async proxy
@@ -269,10 +273,10 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
 
     if (warp < AT_SOFTMAX_WARPS) {
         // =========================================================================== softmax + epilogue warpgroups
-        const int grp = warp >> 2, q = warp & 3;                         // group 0: even blocks, group 1: odd blocks
+        const int grp = warp >> 2, q = warp & 3;                         // group g takes the blocks n = g, g + G, g + 2G, ...
         const int row = q * 32 + lane;                                   // row of the query tile = TMEM lane
-        const bool tr = trace != nullptr && lane == 0 && q == 0;
         const int tr_role = grp == 0 ? 0 : 3;
+        const bool tr = trace != nullptr && lane == 0 && q == 0 && grp < 2;
         const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const float sl2 = 0.125f * 1.4426950408889634f;                  // 1/sqrt(64) * log2(e)
         const int ldo = heads * 64;
@@ -280,10 +284,14 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
         // epilogue of tile t: O / (row sum) -> bf16 -> out[row][head*64 ..]; l_fin / m_fin: this thread's share of the row sum
         auto epilogue = [&](int t, float l_fin, float m_fin) {
             float lt = l_fin;
-            if (C::NKB > 1) {
+            if (C::L_PUBLISHERS > 0) {
                 mbar_wait(&bars[B_LREADY], t & 1);
-                const float2 o = sL[(t & 1) * AT_QTILE + row];
-                lt += o.x * ex2_approx((o.y - m_fin) * sl2);
+                const int g_fin = (t * C::NKB + C::NKB - 1) % G;         // the group running this epilogue
+#pragma unroll
+                for (int i = 1; i <= C::L_PUBLISHERS; ++i) {             // the groups of the tile's last blocks before the final one
+                    const float2 o = sL[((t & 1) * G + (g_fin + G - i) % G) * AT_QTILE + row];
+                    lt += o.x * ex2_approx((o.y - m_fin) * sl2);
+                }
             }
             const float inv = 1.0f / lt;
             const uint32_t ob = t % C::OBUF;
@@ -323,14 +331,15 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
         int pend_t = -1;
         float pend_l = 0.f, pend_m = 0.f;
 #pragma unroll 1
-        for (int n = grp; n < C::NBLK; n += 2) {
+        for (int n = grp; n < C::NBLK; n += G) {
             const int t = n / C::NKB, j = n - t * C::NKB;
             const uint32_t k = n % NBUF, u = n / NBUF;                   // S buffer and how often it has been used before
-            // A parity wait only tells the current phase from the previous one.  With an odd number of S buffers the
-            // previous use of buffer k belonged to the OTHER group, so this group has not seen that phase complete: go
+            // A parity wait only tells the current phase from the previous one.  When the number of S buffers is not a
+            // multiple of the number of groups the previous use of buffer k belonged to ANOTHER group, so this group has not
+            // seen that phase complete: go
             // through it first (it normally has completed long ago), or a wait for phase u posted while the barrier is
             // still in phase u - 1 returns at once (NBUF = 1: group 1 polls S_FULL[0] from the start of the kernel).
-            if ((NBUF & 1) && u > 0) mbar_wait(&bars[B_SFULL + k], (u - 1) & 1);
+            if ((NBUF % G) != 0 && u > 0) mbar_wait(&bars[B_SFULL + k], (u - 1) & 1);
             mbar_wait(&bars[B_SFULL + k], u & 1);
             tcgen05_fence_after();
             if (tr) AT_STAMP(tr_role);                                   // S full
@@ -368,6 +377,7 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
                 }
             }
             const float bm = fmaxf(bm0, bm1);
+            if (tr) AT_STAMP(tr_role);                                   // block maximum known
             // ---- the maximum this row is expressed in: the previous block's, unless this block's exceeds it by > 2^8
             float m_use = bm, o_scale = 1.0f;
             if (n > 0) mbar_wait(&bars[B_MREADY], (n - 1) & 1);          // (every block waits: keeps the phases in step)
@@ -378,7 +388,8 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
             }
             sM[row] = m_use;
             mbar_arrive(&bars[B_MREADY]);
-            if (j <= 1) {                                                // this group's first block of the tile (blocks alternate)
+            if (tr) AT_STAMP(tr_role);                                   // row maximum handed on
+            if (j < G) {                                                 // this group's first block of the tile (its blocks are G apart)
                 l = 0.f;
                 m_mine = m_use;
             }
@@ -458,14 +469,15 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
                 epilogue(pend_t, pend_l, pend_m);
                 pend_t = -1;
             }
-            if (C::NKB > 1 && j == C::NKB - 2) {                         // the OTHER group finishes the tile: hand it our share
-                sL[(t & 1) * AT_QTILE + row] = make_float2(l, m_mine);
+            if (C::L_PUBLISHERS > 0 && j != C::NKB - 1 && j + G >= C::NKB) {
+                // this group's last block of the tile, and another group finishes the tile: hand it our share of the row sum
+                sL[((t & 1) * G + grp) * AT_QTILE + row] = make_float2(l, m_mine);
                 mbar_arrive(&bars[B_LREADY]);
             }
             if (j == C::NKB - 1) {
                 // This group owns the epilogue of tile t.  With two O buffers it is deferred until after the group's next
                 // block: waiting here for the last P V product would hold up the other group through the row-maximum chain.
-                if (C::OBUF == 2 && n + 2 < C::NBLK) { pend_t = t; pend_l = l; pend_m = m_mine; }
+                if (C::OBUF == 2 && n + G < C::NBLK) { pend_t = t; pend_l = l; pend_m = m_mine; }
                 else epilogue(t, l, m_mine);
             }
         }
@@ -476,7 +488,7 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
             constexpr uint32_t idesc_o = idesc_bf16_bmn(AT_QTILE, 64);               // O = P V: V MN-major
             constexpr int PV_STEPS = KB / 16;
             uint32_t n_dbg = 0;
-            const bool dbg_pv = false;
+            const bool dbg_pv = (reinterpret_cast<uintptr_t>(trace) & 8) != 0;      // GTAV_ATTN_TRACE address + 8: time every P V product
             const uint64_t desc_q0 = umma_desc_sw128(smem_u32(sQ)), desc_k0 = umma_desc_sw128(smem_u32(sK));
             const uint64_t desc_v0 = umma_desc_sw128(smem_u32(sV));
             auto try_pv = [&](int n) -> bool {                   // O += P(n) V: needs P written (and, first block of a tile, O read out)
@@ -536,7 +548,7 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
         }
     } else {
         // =========================================================================== query-tile loaders
-        const int lt = threadIdx.x - (AT_SOFTMAX_WARPS + 1) * 32;        // 0 .. 63: chunk lt % 8 of rows lt / 8, lt / 8 + 8, ...
+        const int lt = threadIdx.x - KV_THREADS;                         // 0 .. 63: chunk lt % 8 of rows lt / 8, lt / 8 + 8, ...
         const int c = lt & 7;
 #pragma unroll 1
         for (int t = 0; t < C::QTILES; ++t) {
@@ -563,18 +575,19 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
 #undef AT_STAMP
 }
 
-template <int SEQ, int KB, int NBUF, int TMC, int ROT_PAIRS>
+template <int SEQ, int KB, int NBUF, int TMC, int G, int ROT_PAIRS>
 int launch_tc(const bf16* qkv, bf16* out, int groups, int heads, const float2* rot, cudaStream_t s) {
-    using C = AttnCfg<SEQ, KB, NBUF, TMC>;
+    using C = AttnCfg<SEQ, KB, NBUF, TMC, G>;
     static bool configured = false;
-    auto kern = attn_tc_kernel<SEQ, KB, NBUF, TMC, ROT_PAIRS>;
+    auto kern = attn_tc_kernel<SEQ, KB, NBUF, TMC, G, ROT_PAIRS>;
     if (!configured) {
         GTAV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         configured = true;
     }
-    long long* trace = nullptr;                    // GTAV_ATTN_TRACE=<device address of [CTAs][4][64] int64>: scripts/trace_attn.py
+    // GTAV_ATTN_TRACE=<device address of [CTAs][4][64] int64, + 8 to also time every P V product>: scripts/trace_attn.py
+    long long* trace = nullptr;
     if (const char* e = getenv("GTAV_ATTN_TRACE")) trace = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
-    GTAV_CUDA_OK(launch_k(kern, dim3(groups * heads), dim3(AT_THREADS), C::SMEM, s, qkv, out, heads, rot, trace));
+    GTAV_CUDA_OK(launch_k(kern, dim3(groups * heads), dim3(at_threads(G)), C::SMEM, s, qkv, out, heads, rot, trace));
     return 0;
 }
 
@@ -588,12 +601,13 @@ int launch_attention_tc(const bf16* qkv, bf16* out, int groups, int seq, int hea
         // GTAV_ATTN_KB=96 (A/B measurements): 6 key blocks per tile in 4 S buffers instead of 3 blocks of 192 keys in 2
         // (measured 146 us against 128 us for 32 frames: the per-block hand-offs cost more than the extra buffers save)
         const char* e = getenv("GTAV_ATTN_KB");
-        if (e != nullptr && atoi(e) == 96) return launch_tc<576, 96, 4, 512, 16>(qkv, out, groups, heads, rot, s);
-        return launch_tc<576, 192, 2, 512, 16>(qkv, out, groups, heads, rot, s);
+        if (e != nullptr && atoi(e) == 96) return launch_tc<576, 96, 4, 512, 2, 16>(qkv, out, groups, heads, rot, s);
+        if (e != nullptr && atoi(e) == 964) return launch_tc<576, 96, 4, 512, 4, 16>(qkv, out, groups, heads, rot, s);
+        return launch_tc<576, 192, 2, 512, 2, 16>(qkv, out, groups, heads, rot, s);
     }
     // S = 144: one S buffer and one O buffer in 256 TMEM columns, 72 KB of shared memory -> two CTAs per SM hide each other's
     // staging and hand-off latencies (one CTA has only two (tile, block) steps to pipeline)
-    if (seq == 144 && rot_pairs == 32) return launch_tc<144, 144, 1, 256, 32>(qkv, out, groups, heads, rot, s);
+    if (seq == 144 && rot_pairs == 32) return launch_tc<144, 144, 1, 256, 2, 32>(qkv, out, groups, heads, rot, s);
     set_error("attention (tcgen05): unsupported (seq=%d, rot_pairs=%d); built for (144,32) and (576,16)", seq, rot_pairs);
     return -1;
 }

@@ -457,6 +457,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-algorithm comparison leg")
     ap.add_argument("--no-c5", action="store_true", help="skip the 64-rollout strong-scaling leg (BASELINE config 5)")
+    ap.add_argument("--no-c3", action="store_true", help="skip the B=8 legs (BASELINE config 3 and the dense window step at B=8)")
     ap.add_argument("--no-c1", action="store_true", help="skip the product run of BASELINE config 1")
     ap.add_argument("--no-eager", action="store_true", help="skip the torch-eager-on-GPU informational baseline")
     args = ap.parse_args()
@@ -626,6 +627,43 @@ def main():
                                  gemm_roofline=gemm_roofline(dit, B, pk),
                                  note="every step recomputes the whole window; DiT steps only (no VAE), 1 generated frame timed")
         sampler.close()
+        if not args.no_c3 and world == 1 and args.workload == "c2":
+            # BASELINE config 3 (8 action-conditioned rollouts on one GPU): one timed batch of the shipped path, and the
+            # reference's own schedule (dense 5-frame window, M = 5760 rows) for one generated frame - the regime the
+            # north star's ">= 50 % of bf16 tensor peak sustained in DiT attention / MLP" is demonstrated in
+            w3 = WORKLOADS["c3"]
+            B3, gen3 = w3["B"], w3["total"] - w3["n_prompt"]
+            p3, a3 = synthetic_prompt(B3, w3["n_prompt"]).to(dev), w_actions(B3, w3["total"])
+            g3 = rollout_generators(list(range(B3)), dev)
+            s3 = Sampler(dit, vae, noise_steps=w3["steps"], frame_cache=True)
+            s3.generate(p3, a3, w3["n_prompt"] + 2, generator=g3)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            s3.generate(p3, a3, w3["total"], generator=g3)
+            e1.record()
+            torch.cuda.synchronize()
+            ms3 = e0.elapsed_time(e1)
+            lat3 = s3.encode_prompt(p3)
+            s3.close()
+            d3 = Sampler(dit, vae, noise_steps=w3["steps"], frame_cache=False)
+            d3.sample_latents(lat3, a3, w3["n_prompt"] + 1, generator=g3)                      # plans, eager frame, graph capture
+            torch.cuda.synchronize()
+            e0.record()
+            d3.sample_latents(lat3, a3, w3["n_prompt"] + 1, generator=g3)
+            e1.record()
+            torch.cuda.synchronize()
+            ms3d = e0.elapsed_time(e1) / (w3["steps"] + 1)
+            d3.close()
+            line["c3"] = dict(workload=w3["desc"], value=round(B3 * gen3 / (ms3 / 1000.0), 3), unit=UNIT, ms_per_batch=round(ms3, 1),
+                              ms_per_dit_step=round(ms3 / (gen3 * (w3["steps"] + 1)), 4), rows_per_last_frame_step=144 * B3,
+                              dense=dict(ms_per_dit_step=round(ms3d, 4), step_tflops=round(DIT_STEP_GFLOP * B3 / ms3d, 1),
+                                         frac=round(DIT_STEP_GFLOP * B3 / ms3d / pk["tf"], 4), rows=720 * B3,
+                                         note="dense 5-frame window step at B=8 (the reference's schedule): whole DiT step incl. attention, "
+                                              "LayerNorm, conditioning-free backbone; 589.09 GFLOP x 8 / measured time, against the measured sustained bf16 peak"),
+                              note="one timed batch of 8 rollouts incl. VAE encode / decode (device-timed)")
+            del s3, d3, p3, a3
+            torch.cuda.empty_cache()
         c1_cpu = None
         if not args.no_cpu_baseline and world == 1:             # rank 0 at N = 1 only
             c1_cpu = cpu_c1_run()
