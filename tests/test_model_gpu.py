@@ -245,3 +245,43 @@ def test_vae_posterior_moments(golden):
     assert abs(float(z.mean())) < 0.05 and abs(float(z.std()) - 1.0) < 0.05          # mean + std * N(0, 1)
     rec, post2, zz = vae.autoencode(img.cuda(), sample_posterior=False)
     assert rec.shape == (2, 3, 360, 640) and torch.equal(zz, post2.mean)
+
+
+def test_models_built_and_run_under_inference_mode():
+    """The reference's generate.py builds, loads and moves both models under @torch.inference_mode (load_models / main,
+    generate.py:28,69): parameters are then inference tensors (no version counter).  Same results as modules built the
+    normal way; a later load_state_dict re-packs the weights, and a Sampler created before it rebuilds its graphs."""
+    from gtav_b200.model.dit import DiT
+    from gtav_b200.model.vae import AutoencoderKL
+    from gtav_b200.sampler import Sampler
+    sd = make_dit_state(DiTConfig(depth=2), seed=0)
+    vsd = make_vae_state(VAEConfig(enc_depth=1, dec_depth=1), seed=0)
+    x = seeded_randn((1, 3, 16, 18, 32), 61).cuda()
+    t = torch.tensor([[15, 15, 700]]).cuda()
+    z = seeded_randn((1, 576, 16), 62).cuda()
+    _, ref_dit = dit_pair(2)
+    _, ref_vae = vae_pair(1, 1)
+    v_ref, d_ref = ref_dit(x, t), ref_vae.decode(z)
+    with torch.inference_mode():
+        dit = DiT(depth=2)
+        dit.load_state_dict(sd, strict=True)
+        vae = AutoencoderKL(latent_dim=16, patch_size=20, enc_dim=1024, enc_depth=1, enc_heads=16, dec_dim=1024, dec_depth=1,
+                            dec_heads=16, input_height=360, input_width=640)
+        vae.load_state_dict(vsd, strict=True)
+        dit, vae = dit.cuda().eval(), vae.cuda().eval()
+        assert all(p.is_inference() for p in dit.parameters())
+        assert torch.equal(dit(x, t), v_ref) and torch.equal(vae.decode(z), d_ref)
+        # a Sampler that has run, then new weights: the packed copies, plans and captured graphs are rebuilt, not reused
+        s = Sampler(dit, None, noise_steps=2)
+        prompt = x[:, :2].float()
+        noise = seeded_randn((1, 1, 16, 18, 32), 63).cuda()
+        a = s.sample_latents(prompt, None, 3, noise=noise)
+        sd2 = make_dit_state(DiTConfig(depth=2), seed=5)
+        dit.load_state_dict(sd2, strict=True)
+        b = s.sample_latents(prompt, None, 3, noise=noise)
+        fresh = DiT(depth=2)
+        fresh.load_state_dict(sd2, strict=True)
+        fresh = fresh.cuda().eval()
+        c = Sampler(fresh, None, noise_steps=2).sample_latents(prompt, None, 3, noise=noise)
+        assert not torch.equal(a, b), "the sampler kept replaying graphs built on the old weights"
+        assert torch.equal(b, c)
