@@ -23,7 +23,7 @@ def main():
         m = re.search(r"Function : (\S+)", line)
         if m:
             cur = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip() or m.group(1)
-            cur = re.sub(r"\(.*", "", cur)[:110]
+            cur = re.sub(r"\(.*", "", cur.replace("(anonymous namespace)::", ""))[:110]
             order.append(cur)
             continue
         if cur is None:
