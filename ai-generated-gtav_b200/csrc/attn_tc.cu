@@ -39,8 +39,11 @@ namespace {
 
 constexpr int AT_GROUP_WARPS = 4;                     // one softmax warpgroup = 128 query rows (one warp per TMEM lane quadrant)
 constexpr int AT_LOADER_WARPS = 2;
-constexpr int AT_MMA_WARPS = 1;                       // one thread issues every MMA (two issuing threads, one per product, were
-                                                      // measured: 134 vs 127 us for 32 frames, and no gain from either ordering)
+constexpr int AT_MMA_WARPS = 1;                       // one thread issues every MMA.  Measured alternatives (32 VAE frames, this
+                                                      // kernel 127 us): one issuing thread per product with blocking waits 134 us
+                                                      // (and, with 96-key blocks in four buffers, a hang in later-wave CTAs that
+                                                      // was not understood); 96-key blocks with a fixed issue order and blocking
+                                                      // waits 162 us, with the polling scheduler 146 us; four softmax groups 146 us
 __host__ __device__ constexpr int at_threads(int groups) { return (groups * AT_GROUP_WARPS + AT_MMA_WARPS + AT_LOADER_WARPS) * 32; }   // 352 (2 groups)
 constexpr int AT_QTILE = 128;
 constexpr int AT_ROWB = 128;                          // bytes per staged row (64 bf16)

@@ -113,8 +113,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 26)) {
-            printf("gtav: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y,
-                   threadIdx.x, parity);
+            printf("gtav: mbarrier wait timed out (block %d,%d thread %d parity %u, barrier at shared offset %u)\n", blockIdx.x, blockIdx.y,
+                   threadIdx.x, parity, smem_u32(bar));
             __trap();
         }
     }
