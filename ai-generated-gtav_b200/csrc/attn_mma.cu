@@ -50,15 +50,16 @@ attn_seq144_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int hea
 // Which implementation runs (measured on B200, scripts/bench_attn.py, profiles/r02/bench_attn_*.log):
 //   S = 576 (VAE): the tcgen05 kernel (attn_tc.cu) from 4 frames up (64 CTAs): 128 us against 222 us for 32 frames; below
 //                  that one CTA per head leaves most SMs idle and the mma.sync kernel's 9 CTAs per head win (23 vs 31 us);
-//   S = 144 (DiT): the tcgen05 kernel from 40 frames up (dense windows of 8 rollouts, context passes, 64-rollout steps),
-//                  where the two are within 5 % of each other (230 vs 238 us at 320 frames); the latency-bound last-frame
-//                  steps of few rollouts stay on the mma.sync kernel (5 us against 11 us per launch at one frame).
+//   S = 144 (DiT): the tcgen05 kernel from 96 frames up (context passes and dense windows of >= 20 rollouts), where it is
+//                  2-3 % ahead (120 vs 123 us at 160 frames, 233 vs 238 us at 320; cross-over at ~96: 76.6 vs 77.1 us); below
+//                  that the mma.sync kernel's 3 CTAs per head win, most clearly in the latency-bound last-frame steps of few
+//                  rollouts (5 us against 11 us per launch at one frame, 35 vs 38 us at 40 frames).
 // GTAV_ATTN = "tc" / "mma" forces one of them for every size (parity tests, A/B measurements).
 static int attn_use_tc(int seq, int groups) {
     const char* e = getenv("GTAV_ATTN");          // read per call: launches are captured into graphs, tests flip it
     if (e != nullptr && e[0] == 't') return 1;
     if (e != nullptr && e[0] == 'm') return 0;
-    return seq == 576 ? groups >= 4 : groups >= 40;
+    return seq == 576 ? groups >= 4 : groups >= 96;
 }
 
 int launch_attention_seq(const bf16* qkv, bf16* out, int groups, int seq, int heads, const float2* rot, int rot_pairs,

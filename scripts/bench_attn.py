@@ -35,7 +35,7 @@ def run(seq, pairs, groups, impl, reps=20):
     return us, fl / us / 1e6
 
 
-for seq, pairs, groups in ((576, 16, 1), (576, 16, 4), (576, 16, 32), (576, 16, 64), (144, 32, 1), (144, 32, 5), (144, 32, 40), (144, 32, 320)):
+for seq, pairs, groups in ((576, 16, 1), (576, 16, 4), (576, 16, 32), (576, 16, 64), (144, 32, 1), (144, 32, 5), (144, 32, 40), (144, 32, 64), (144, 32, 96), (144, 32, 160), (144, 32, 256), (144, 32, 320)):
     row = []
     for impl in ("mma", "tc"):
         us, tf = run(seq, pairs, groups, impl)
