@@ -1,5 +1,5 @@
-// Device body of the fused-rotary non-causal attention (see attn_mma.cu for the op it replaces): shared by the
-// stand-alone attn_seq_kernel and the persistent last-frame step kernel (dit_step_mega.cu).
+// Device body of the fused-rotary non-causal attention on mma.sync tiles (see attn_mma.cu for the op it replaces and for when
+// it runs instead of the tcgen05 kernel of attn_tc.cu), shared by attn_seq_kernel and attn_seq144_kernel.
 #pragma once
 #include "common.cuh"
 #include "kernels.h"

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: generated frames/sec end-to-end (100-step DiT + VAE decode), BASELINE.json.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c1|c5]
 
 A *step* is one complete rollout batch of the README inference shape (BASELINE config 2: B=1 rollout,
 32 frames, 4 prompt frames, 100 noise steps => 28 generated frames x 101 DiT evaluations, plus VAE
@@ -14,10 +14,15 @@ kernels).  One JSON line is printed by rank 0:
            against the measured HBM bandwidth: algorithmic bytes of its 128 launches per step / their CUDA-event time
            (weights HBM-cold, as in the real step); at B > 1 and in the `dense` leg the tiled / CTA-pair GEMM against
            the measured sustained bf16 tensor throughput
-  cpu_baseline: the CPU port of the reference (oracle/) timed on this box's host cores on a bounded sample
+  c5     : BASELINE config 5 on every N - 64 rollouts sharded r % world, one timed batch (strong scaling)
+  c3, dense, c1, cpu_baseline, gpu_eager_baseline (N = 1 only): config 3 and the dense B = 8 window step; the
+           reference's schedule at B = 1; config 1 through the product beside the CPU run of the same config; the CPU
+           port of the reference (oracle/) timed on this box's host cores on config 1 in full; the reference's graph in
+           torch eager on this GPU (informational)
 With --impl reference only the CPU arm runs (the Python reference cannot travel to the GPU box; the
 oracle port is its restatement) and prints the same line with "impl": "reference".
-N > 1 (torchrun): every rank runs its own rollouts (weak scaling, no collective on the data path).
+N > 1 (torchrun): every rank runs its own rollouts (weak scaling, no collective on the data path); every collective
+of this file is in barrier() / timed(), called the same number of times by every rank.
 """
 from __future__ import annotations
 
