@@ -21,8 +21,9 @@
 //   * optionally the reduce is done per token row by every CTA (plus reduce-only CTAs up to one per token), which lets
 //     the row-wise kernel that would follow - LayerNorm + modulate, or the last-frame temporal attention - run inside
 //     it; everything those need besides the partial sums is loaded BEFORE the rendezvous.
-// Warp roles (256 threads): 0 = W producer, 1 = A producer, 2 = TMEM allocator + MMA issuer, 4-7 = L2 prefetch of
-// the next GEMM's weights; all 8 warps drain the accumulator (one TMEM lane quadrant each, half of the columns) and reduce.
+// Warp roles (256 threads): 0 = W producer, 1 = A producer, 2 = TMEM allocator + MMA issuer; all 8 warps drain the
+// accumulator (one TMEM lane quadrant each, half of the columns) and reduce.  (An optional L2 prefetch of the next GEMM's
+// weights, issued once the accumulator is complete, is off by default: GemmParams::prefetch, see dit_engine.cu.)
 #include "attn_temporal_core.cuh"
 #include "common.cuh"
 #include "kernels.h"
@@ -479,10 +480,10 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         mbar_wait(bar_acc, 0);
         tcgen05_fence_after();
         if (threadIdx.x == 128) SK_STAMP(4);                                   // accumulator complete
-        // This CTA's operand slab has been consumed and HBM is idle for the rest of the launch (partials, rendezvous and
-        // reduce only move data through L2): pull the NEXT GEMM's weights into L2 now, so that its slab request - issued
-        // when its CTAs start, ~5 us from here - is an L2 hit instead of an HBM round trip at the head of its critical
-        // path.  (Issued at kernel start, round 1, the prefetch competed with this launch's own slab loads and cost 1.5 %.)
+        // Optional (GTAV_PREFETCH=1; null by default): this CTA's operand slab has been consumed and HBM is idle for the
+        // rest of the launch (partials, rendezvous and reduce only move data through L2), so the NEXT GEMM's weights can be
+        // pulled into L2 here.  Measured: 1.191 vs 1.169 ms per last-frame step - the next launch's weight slab is not what
+        // its critical path waits for (its token slab lands at the same time); issued at kernel start (round 1) it cost 1.5 %.
         l2_prefetch_share(p.g.prefetch, p.g.prefetch_bytes, blockIdx.x * SK_THREADS + threadIdx.x, p.gemm_ctas * SK_THREADS);
         const int c0 = warp < 4 ? half : 0;
         const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0;
