@@ -39,7 +39,7 @@ namespace {
 
 constexpr int AT_GROUP_WARPS = 4;                     // one softmax warpgroup = 128 query rows (one warp per TMEM lane quadrant)
 constexpr int AT_LOADER_WARPS = 2;
-constexpr int AT_MMA_WARPS = 1;                       // one thread issues every MMA.  Measured alternatives (32 VAE frames, this
+constexpr int AT_MMA_WARPS = 1;                       // one warp (one elected lane) issues every MMA.  Measured alternatives (32 VAE frames, this
                                                       // kernel 127 us): one issuing thread per product with blocking waits 134 us
                                                       // (and, with 96-key blocks in four buffers, a hang in later-wave CTAs that
                                                       // was not understood); 96-key blocks with a fixed issue order and blocking
@@ -485,8 +485,13 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
             }
         }
         } else if (warp == AT_SOFTMAX_WARPS) {
-        // =========================================================================== MMA issuer (one thread)
-        if (lane == 0) {
+        // =========================================================================== MMA issuer (one warp, one elected lane)
+        // WARP-UNIFORM control flow: all 32 lanes run the scheduler and probe the barriers, the decisions are made uniform
+        // with a vote and elect.sync picks the lane that issues.  Inside `if (lane == 0)` the compiler keeps descriptors and
+        // addresses in vector registers and moves them to uniform registers per tcgen05.mma: ~106 instead of ~76 cycles per
+        // small MMA, and every barrier probe of the lone thread ~170 cycles (scripts/probe_umma_chunks.cu) - the P V product
+        // is 12 MMAs of 61 cycles per block, so the issuing thread was the limiter.
+        {
             constexpr uint32_t idesc_s = umma_idesc_bf16(AT_QTILE, KB);              // S = Q K^T: both operands K-major
             constexpr uint32_t idesc_o = idesc_bf16_bmn(AT_QTILE, 64);               // O = P V: V MN-major
             constexpr int PV_STEPS = KB / 16;
@@ -494,46 +499,57 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
             const bool dbg_pv = (reinterpret_cast<uintptr_t>(trace) & 8) != 0;      // GTAV_ATTN_TRACE address + 8: time every P V product
             const uint64_t desc_q0 = umma_desc_sw128(smem_u32(sQ)), desc_k0 = umma_desc_sw128(smem_u32(sK));
             const uint64_t desc_v0 = umma_desc_sw128(smem_u32(sV));
-            auto try_pv = [&](int n) -> bool {                   // O += P(n) V: needs P written (and, first block of a tile, O read out)
+            auto ready_pv = [&](int n) -> bool {                 // O += P(n) V: needs P written (and, first block of a tile, O read out)
                 const int t = n / C::NKB, j = n - t * C::NKB;
                 const uint32_t k = n % NBUF, ob = t % C::OBUF;
                 if (j == 0 && t >= C::OBUF && !mbar_test(&bars[B_OFREE + ob], (t / C::OBUF - 1) & 1)) return false;
-                if (!mbar_test(&bars[B_PREADY + k], (n / NBUF) & 1)) return false;
+                return mbar_test(&bars[B_PREADY + k], (n / NBUF) & 1);
+            };
+            auto issue_pv = [&](int n) {
+                const int t = n / C::NKB, j = n - t * C::NKB;
+                const uint32_t k = n % NBUF, ob = t % C::OBUF;
                 tcgen05_fence_after();
-                AT_STAMP(1);                       // P ready
                 const uint32_t d = tmem_base + C::TM_O + ob * 64;
                 const uint32_t pa = tmem_base + k * C::S_COLS;                   // P(n): 8 columns per K step of 16 keys
-                // B descriptors = a base built once + compile-time offsets (16-byte units): the issuing thread's own scalar
-                // code is what bounds a short MMA (scripts/probe_umma_pv.cu: ~100 cycles per MMA with the descriptor
-                // rebuilt in the loop, ~61 with it precomputed)
+                // B descriptors = a base built once + compile-time offsets (16-byte units)
                 const uint64_t db0 = desc_v0 + static_cast<uint64_t>(j * (KB * AT_ROWB / 16));
+                if (elect_one()) {
+                    AT_STAMP(1);                   // P ready
 #pragma unroll
-                for (int ks = 0; ks < PV_STEPS; ++ks)
-                    umma_bf16_ts(d, pa + ks * 8, db0 + ks * (16 * AT_ROWB / 16), idesc_o, (j | ks) != 0 ? 1u : 0u);
-                umma_commit(&bars[B_SFREE + k]);                                 // S buffer (and the P inside it) consumed
-                if (j == C::NKB - 1) umma_commit(&bars[B_OFULL + ob]);
-                if (trace != nullptr && dbg_pv) {  // profiling only: time the product itself
-                    umma_commit(&bars[B_DBG]);
-                    mbar_wait(&bars[B_DBG], n_dbg++ & 1);
-                    AT_STAMP(1);                   // P V done
+                    for (int ks = 0; ks < PV_STEPS; ++ks)
+                        umma_bf16_ts(d, pa + ks * 8, db0 + ks * (16 * AT_ROWB / 16), idesc_o, (j | ks) != 0 ? 1u : 0u);
+                    umma_commit(&bars[B_SFREE + k]);                             // S buffer (and the P inside it) consumed
+                    if (j == C::NKB - 1) umma_commit(&bars[B_OFULL + ob]);
+                    if (trace != nullptr && dbg_pv) {  // profiling only: time the product itself
+                        umma_commit(&bars[B_DBG]);
+                        mbar_wait(&bars[B_DBG], n_dbg++ & 1);
+                        AT_STAMP(1);               // P V done
+                    }
                 }
-                return true;
+                __syncwarp();
             };
-            auto try_s = [&](int n) -> bool {                    // S(n) = Q K^T: needs the query tile staged and the S buffer consumed
+            auto ready_s = [&](int n) -> bool {                  // S(n) = Q K^T: needs the query tile staged and the S buffer consumed
                 const int t = n / C::NKB, j = n - t * C::NKB;
                 const uint32_t k = n % NBUF;
                 if (j == 0 && !mbar_test(&bars[B_QFULL + (t & 1)], (t >> 1) & 1)) return false;
                 if (n >= NBUF && !mbar_test(&bars[B_SFREE + k], (n / NBUF - 1) & 1)) return false;
+                return true;
+            };
+            auto issue_s = [&](int n) {
+                const int t = n / C::NKB, j = n - t * C::NKB;
+                const uint32_t k = n % NBUF;
                 tcgen05_fence_after();
                 const uint32_t d = tmem_base + k * C::S_COLS;
                 const uint64_t da0 = desc_q0 + static_cast<uint64_t>((t & 1) * (C::Q_BYTES / 16));
                 const uint64_t db0 = desc_k0 + static_cast<uint64_t>(j * (KB * AT_ROWB / 16));
+                if (elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(d, da0 + 2 * kk, db0 + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
-                umma_commit(&bars[B_SFULL + k]);
-                if (j == C::NKB - 1) umma_commit(&bars[B_QFREE + (t & 1)]);          // last read of this query tile
-                AT_STAMP(1);                       // S(n) issued
-                return true;
+                    for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(d, da0 + 2 * kk, db0 + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
+                    umma_commit(&bars[B_SFULL + k]);
+                    if (j == C::NKB - 1) umma_commit(&bars[B_QFREE + (t & 1)]);      // last read of this query tile
+                    AT_STAMP(1);                   // S(n) issued
+                }
+                __syncwarp();
             };
             // Whichever of the two next products has its operands ready is issued, S first: an S tile must not queue behind
             // a P V product that is still waiting for its probabilities - the softmax group that owns the buffer would sit
@@ -543,10 +559,20 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
             uint32_t idle = 0;
             while (next_pv < C::NBLK) {
                 bool did = false;
-                if (next_s < C::NBLK && try_s(next_s)) { ++next_s; did = true; }
-                else if (next_pv < next_s && try_pv(next_pv)) { ++next_pv; did = true; }
+                if (next_s < C::NBLK && __all_sync(0xffffffffu, ready_s(next_s))) {
+                    issue_s(next_s);
+                    ++next_s;
+                    did = true;
+                } else if (next_pv < next_s && __all_sync(0xffffffffu, ready_pv(next_pv))) {
+                    issue_pv(next_pv);
+                    ++next_pv;
+                    did = true;
+                }
                 if (did) idle = 0;
-                else if (++idle > (1u << 26)) { printf("gtav: attention MMA scheduler stalled (block %d)\n", blockIdx.x); __trap(); }
+                else if (++idle > (1u << 26)) {
+                    if (lane == 0) printf("gtav: attention MMA scheduler stalled (block %d)\n", blockIdx.x);
+                    __trap();
+                }
             }
         }
     } else {

@@ -25,17 +25,18 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     return __bfloat1622float2(v);
 }
 
-// GELU(tanh): 0.5 x (1 + tanh(beta (x + kappa x^3))) as torch evaluates it in fp32 (aten/native/cuda/
-// ActivationGeluKernel.cu), with tanh(u) = 1 - 2 / (exp(2u) + 1) on the fast exp / divide units instead of tanhf:
-// ~1e-6 relative, far inside the bf16 rounding the result gets, and ~6x fewer instructions - tanhf made the fc1
-// epilogue the slowest phase of the weight-streaming GEMM's reduce (2.0 vs 1.2 us) and of the tiled GEMM's tile loop.
+// GELU(tanh): 0.5 x (1 + tanh(u)), u = beta (x + kappa x^3), as torch evaluates it in fp32 (aten/native/cuda/
+// ActivationGeluKernel.cu) - written as x * sigmoid(2u) = x / (1 + 2^(-2u log2 e)): seven instructions (one ex2, one rcp on
+// the fast units) instead of tanhf's ~40 or the 14 of 1 - 2 / (exp(2u) + 1), no cancellation near 0, ~3e-7 relative - far
+// inside the bf16 rounding the result gets.  The GELU epilogue is ALU-bound (fc1 of the weight-streaming GEMM's reduce,
+// the tiled GEMM's tile loop at K = 1024), so its instruction count is step time.
 __device__ __forceinline__ float gelu_tanh_f(float x) {
-    const float kBeta = 0.7978845608028654f;   // sqrt(2/pi)
+    const float kC1 = 2.0f * 0.7978845608028654f * 1.4426950408889634f;   // 2 beta log2(e)
     const float kKappa = 0.044715f;
-    const float inner = kBeta * (x + kKappa * x * x * x);
-    const float e = __expf(2.0f * inner);      // +inf for large inner: 2 / inf = 0, tanh = 1
-    const float t = 1.0f - __fdividef(2.0f, e + 1.0f);
-    return 0.5f * x * (1.0f + t);
+    const float w = fmaf(x * x, kKappa * kC1, kC1);                        // 2 beta log2(e) (1 + kappa x^2)
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-x * w));
+    return __fdividef(x, 1.0f + e);                                        // e = +inf for very negative x: x / inf = -0
 }
 __device__ __forceinline__ float gelu_erf_f(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f));

@@ -411,26 +411,36 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     pdl_trigger();
     if (!gemm_cta && threadIdx.x == 128) SK_STAMP(1);                          // set-up done
     if (gemm_cta && warp == 2) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, SK_NT);
-            mbar_wait(bar_w, 0);
-            SK_STAMP(2);                                                       // W slab landed
+        // warp-uniform control flow, elect.sync picks the issuing lane: inside `if (lane == 0)` every tcgen05.mma cost the lone
+        // thread ~106 cycles (descriptors moved from vector to uniform registers per instruction) against the 75 the tensor
+        // pipe needs for 128 x 144 x 16 (scripts/probe_umma_chunks.cu)
+        constexpr uint32_t idesc = umma_idesc_bf16(128, SK_NT);
+        const uint64_t dw0 = umma_desc_sw128(smem_u32(sW));
+        const uint64_t da0 = umma_desc_sw128(smem_u32(sA));
+        mbar_wait(bar_w, 0);
+        if (lane == 0) SK_STAMP(2);                                            // W slab landed
 #pragma unroll 1
-            for (int t = 0; t < tiles; ++t) {
-                mbar_wait(&bar_a[t], 0);
-                if (t == 0) SK_STAMP(3);                                       // first A tile landed
-                tcgen05_fence_after();
+        for (int t = 0; t < tiles; ++t) {
+            mbar_wait(&bar_a[t], 0);
+            if (t == 0 && lane == 0) SK_STAMP(3);                              // first A tile landed
+            tcgen05_fence_after();
+            // (the chunk loop stays OUTSIDE the elected branch: descriptor arithmetic runs on the uniform datapath only where
+            // control flow is warp-uniform)
+            uint64_t dw = dw0, da = da0 + static_cast<uint64_t>(t * chunks * (SK_A_CHUNK >> 4));
 #pragma unroll 1
-                for (int ch = 0; ch < chunks; ++ch) {
-                    const uint64_t dw = umma_desc_sw128(smem_u32(sW + ch * SK_W_CHUNK));
-                    const uint64_t da = umma_desc_sw128(smem_u32(sA + (t * chunks + ch) * SK_A_CHUNK));
+            for (int ch = 0; ch < chunks; ++ch) {
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         umma_bf16_ss(tmem_base + t * SK_NT, dw + 2 * k, da + 2 * k, idesc, (ch | k) != 0 ? 1u : 0u);
                 }
+                __syncwarp();
+                dw += SK_W_CHUNK >> 4;
+                da += SK_A_CHUNK >> 4;
             }
-            umma_commit(bar_acc);
         }
+        if (elect_one()) umma_commit(bar_acc);
+        __syncwarp();
         pdl_wait();
     } else {
         pdl_wait();

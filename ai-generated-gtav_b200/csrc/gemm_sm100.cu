@@ -92,64 +92,85 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     pdl_trigger();                                // the next kernel may start its own set-up now
 
     if (warp == 0 || warp == 7) {
-        // A producers: thread j (warp 0 -> j = 0, warp 7 -> j = 1) loads K chunk j of every stage
+        // A producers: warp j (warp 0 -> j = 0, warp 7 -> j = 1) loads K chunk j of every stage.  Warp-uniform loops, one
+        // elected lane issues (same reason as the MMA warp below); ring position kept as a counter.
         const int j = warp == 0 ? 0 : 1;
         pdl_wait();                               // A is the previous kernel's output
-        if (lane == 0 && j < KC) {
-            int it = 0;
+        if (j < KC) {
+            int s = 0;
+            uint32_t ph = 1;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int m_blk = tile / n_tiles_n;
-                for (int ks = 0; ks < num_ks; ++ks, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[s], L::A_CHUNK);
-                    tma_load_2d(sA + s * L::A_BYTES + j * L::A_CHUNK, &tmA, &full_bar[s], (ks * KC + j) * BK, m_blk * BM);
+                for (int ks = 0; ks < num_ks; ++ks) {
+                    mbar_wait(&empty_bar[s], ph);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&full_bar[s], L::A_CHUNK);
+                        tma_load_2d(sA + s * L::A_BYTES + j * L::A_CHUNK, &tmA, &full_bar[s], (ks * KC + j) * BK, m_blk * BM);
+                    }
+                    __syncwarp();
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 6 || warp == 8) {
         // W producers, the same split; weights are never written by the kernel before us: stream them without waiting
         const int j = warp == 6 ? 0 : 1;
-        if (lane == 0 && j < KC) {
-            int it = 0;
+        if (j < KC) {
+            int s = 0;
+            uint32_t ph = 1;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int n_blk = tile % n_tiles_n;
-                for (int ks = 0; ks < num_ks; ++ks, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[s], L::B_CHUNK);
-                    tma_load_2d(sB + s * L::B_BYTES + j * L::B_CHUNK, &tmB, &full_bar[s], (ks * KC + j) * BK, n_blk * BN);
+                for (int ks = 0; ks < num_ks; ++ks) {
+                    mbar_wait(&empty_bar[s], ph);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&full_bar[s], L::B_CHUNK);
+                        tma_load_2d(sB + s * L::B_BYTES + j * L::B_CHUNK, &tmB, &full_bar[s], (ks * KC + j) * BK, n_blk * BN);
+                    }
+                    __syncwarp();
+                    if (++s == STAGES) { s = 0; ph ^= 1u; }
                 }
             }
         }
         pdl_wait();
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-            int it = 0, local = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
-                const int acc = local & 1;
-                mbar_wait(&tempty_bar[acc], ((local >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+        // MMA issue with WARP-UNIFORM control flow: all 32 lanes run the loops and wait on the barriers, elect.sync picks the
+        // issuing lane.  Inside `if (lane == 0)` the compiler keeps descriptors in vector registers and moves them to
+        // uniform registers per tcgen05.mma, and every barrier probe of the lone thread costs ~170 cycles: measured
+        // 106 -> 76 cycles per small MMA and 43 -> 7 cycles per MMA for one wait per four (scripts/probe_umma_chunks.cu) -
+        // with 8 MMAs of 130 cycles per stage the lone thread was as slow as the tensor pipe.  Descriptors are a base
+        // plus compile-time offsets; the ring position is a counter, not it % STAGES.
+        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+        const uint64_t da0 = umma_desc_sw128(smem_u32(sA));
+        const uint64_t db0 = umma_desc_sw128(smem_u32(sB));
+        int s = 0, local = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+            const int acc = local & 1;
+            mbar_wait(&tempty_bar[acc], ((local >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
+            tcgen05_fence_after();
+            const uint32_t tmem_acc = tmem_base + acc * BN;
+            for (int ks = 0; ks < num_ks; ++ks) {
+                mbar_wait(&full_bar[s], ph);
                 tcgen05_fence_after();
-                const uint32_t tmem_acc = tmem_base + acc * BN;
-                for (int ks = 0; ks < num_ks; ++ks, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
-                    tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint64_t da = da0 + static_cast<uint64_t>(s * (L::A_BYTES >> 4));
+                    const uint64_t db = db0 + static_cast<uint64_t>(s * (L::B_BYTES >> 4));
 #pragma unroll
                     for (int c = 0; c < KC; ++c) {
-                        const uint64_t da = umma_desc_sw128(smem_u32(sA + s * L::A_BYTES + c * L::A_CHUNK));
-                        const uint64_t db = umma_desc_sw128(smem_u32(sB + s * L::B_BYTES + c * L::B_CHUNK));
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) {
                             // +32 bytes (16 bf16) along K inside the 128-byte swizzle row: +2 in 16-byte units
-                            umma_bf16_ss(tmem_acc, da + 2 * k, db + 2 * k, idesc, (ks | c | k) != 0 ? 1u : 0u);
+                            umma_bf16_ss(tmem_acc, da + (c * (L::A_CHUNK >> 4) + 2 * k), db + (c * (L::B_CHUNK >> 4) + 2 * k), idesc,
+                                         (ks | c | k) != 0 ? 1u : 0u);
                         }
                     }
                     umma_commit(&empty_bar[s]);       // slot reusable once these MMAs have read it
                 }
-                umma_commit(&tfull_bar[acc]);         // accumulator complete
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
             }
+            if (elect_one()) umma_commit(&tfull_bar[acc]);     // accumulator complete
+            __syncwarp();
         }
         pdl_wait();
     } else {

@@ -135,59 +135,74 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     pdl_trigger();
 
     if (warp == 0 || warp == 7) {
+        // producers: warp-uniform loops, one elected lane issues; ring position kept as a counter
         const int j = warp == 0 ? 0 : 1;
         pdl_wait();                                   // A is the previous kernel's output
-        if (lane == 0) {
-            int it = 0;
-            for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
-                const int m_row = ((tile / n_tiles_n) * 2 + static_cast<int>(rank)) * G2_BM;
-                for (int ks = 0; ks < num_ks; ++ks, ++it) {
-                    const int s = it % G2_STAGES;
-                    mbar_wait(&empty_bar[s], ((it / G2_STAGES) & 1) ^ 1);
+        int s = 0;
+        uint32_t ph = 1;
+        for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+            const int m_row = ((tile / n_tiles_n) * 2 + static_cast<int>(rank)) * G2_BM;
+            for (int ks = 0; ks < num_ks; ++ks) {
+                mbar_wait(&empty_bar[s], ph);
+                if (elect_one()) {
                     if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * G2_A_CHUNK);
                     tma_load_2d_pair(sA + (s * G2_KC + j) * G2_A_CHUNK, &tmA, &full_bar[s], (ks * G2_KC + j) * G2_BK, m_row);
                 }
+                __syncwarp();
+                if (++s == G2_STAGES) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 6 || warp == 8) {
         const int j = warp == 6 ? 0 : 1;
-        if (lane == 0) {
-            int it = 0;
-            for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
-                const int n_row = (tile % n_tiles_n) * G2_BN + static_cast<int>(rank) * (G2_BN / 2);
-                for (int ks = 0; ks < num_ks; ++ks, ++it) {
-                    const int s = it % G2_STAGES;
-                    mbar_wait(&empty_bar[s], ((it / G2_STAGES) & 1) ^ 1);
+        int s = 0;
+        uint32_t ph = 1;
+        for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+            const int n_row = (tile % n_tiles_n) * G2_BN + static_cast<int>(rank) * (G2_BN / 2);
+            for (int ks = 0; ks < num_ks; ++ks) {
+                mbar_wait(&empty_bar[s], ph);
+                if (elect_one()) {
                     if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * G2_B_CHUNK);
                     tma_load_2d_pair(sB + (s * G2_KC + j) * G2_B_CHUNK, &tmB, &full_bar[s], (ks * G2_KC + j) * G2_BK, n_row);
                 }
+                __syncwarp();
+                if (++s == G2_STAGES) { s = 0; ph ^= 1u; }
             }
         }
         pdl_wait();
     } else if (warp == 1) {
-        if (leader && lane == 0) {
+        if (leader) {
+            // warp-uniform control flow, elect.sync picks the issuing lane (see gemm_sm100.cu: the lone-thread form of this
+            // loop paid ~100 cycles of its own per MMA and ~170 per barrier probe)
             constexpr uint32_t idesc = umma_idesc_bf16(2 * G2_BM, G2_BN);
-            int it = 0, local = 0;
+            const uint64_t da0 = umma_desc_sw128(smem_u32(sA));
+            const uint64_t db0 = umma_desc_sw128(smem_u32(sB));
+            int s = 0, local = 0;
+            uint32_t ph = 0;
             for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++local) {
                 const int acc = local & 1;
                 mbar_wait(&tempty_bar[acc], ((local >> 1) & 1) ^ 1);      // both CTAs have drained this accumulator
                 tcgen05_fence_after();
                 const uint32_t tmem_acc = tmem_base + acc * G2_BN;
-                for (int ks = 0; ks < num_ks; ++ks, ++it) {
-                    const int s = it % G2_STAGES;
-                    mbar_wait(&full_bar[s], (it / G2_STAGES) & 1);
+                for (int ks = 0; ks < num_ks; ++ks) {
+                    mbar_wait(&full_bar[s], ph);
                     tcgen05_fence_after();
+                    if (elect_one()) {
+                        const uint64_t da = da0 + static_cast<uint64_t>(s * ((G2_KC * G2_A_CHUNK) >> 4));
+                        const uint64_t db = db0 + static_cast<uint64_t>(s * ((G2_KC * G2_B_CHUNK) >> 4));
 #pragma unroll
-                    for (int c = 0; c < G2_KC; ++c) {
-                        const uint64_t da = umma_desc_sw128(smem_u32(sA + (s * G2_KC + c) * G2_A_CHUNK));
-                        const uint64_t db = umma_desc_sw128(smem_u32(sB + (s * G2_KC + c) * G2_B_CHUNK));
+                        for (int c = 0; c < G2_KC; ++c) {
 #pragma unroll
-                        for (int k = 0; k < G2_BK / 16; ++k)
-                            umma_bf16_ss_pair(tmem_acc, da + 2 * k, db + 2 * k, idesc, (ks | c | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < G2_BK / 16; ++k)
+                                umma_bf16_ss_pair(tmem_acc, da + (c * (G2_A_CHUNK >> 4) + 2 * k), db + (c * (G2_B_CHUNK >> 4) + 2 * k), idesc,
+                                                  (ks | c | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit_pair(&empty_bar[s]);  // slot reusable in both CTAs once these MMAs have read it
                     }
-                    umma_commit_pair(&empty_bar[s]);  // slot reusable in both CTAs once these MMAs have read it
+                    __syncwarp();
+                    if (++s == G2_STAGES) { s = 0; ph ^= 1u; }
                 }
-                umma_commit_pair(&tfull_bar[acc]);    // accumulator halves complete in both CTAs
+                if (elect_one()) umma_commit_pair(&tfull_bar[acc]);    // accumulator halves complete in both CTAs
+                __syncwarp();
             }
         }
         pdl_wait();
