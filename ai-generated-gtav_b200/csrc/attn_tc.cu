@@ -11,11 +11,13 @@
 //     image of V is the MN-major B operand of O = P V (no transpose anywhere);
 //   * queries are processed in tiles of 128 rows (UMMA M = 128), staged the same way by two loader warps into a
 //     double-buffered slot while the previous tile is being worked on;
-//   * the (query tile, key block) pairs form ONE flat sequence n = 0, 1, ...: the MMA thread issues S(n + 1) = Q K^T
-//     into the double-buffered TMEM S region before the P V product of block n, and the two softmax warpgroups take the
-//     blocks alternately (warps 0-3 the even n, warps 4-7 the odd n; thread = query row = TMEM lane), so that one
-//     group's TMEM loads, shared-memory stores and barrier waits run under the other group's exponentials - the MUFU
-//     pipe (one ex2 per score, 16 per clock per SM) is the bound of this kernel;
+//   * the (query tile, key block) pairs form ONE flat sequence n = 0, 1, ...: the MMA warp issues S(n + 1), S(n + 2) = Q K^T
+//     into a ring of TMEM S buffers ahead of the P V product of block n, and the softmax warpgroups take the blocks round
+//     robin (group g the blocks n = g mod G; thread = query row = TMEM lane), so that one group's TMEM loads, stores and
+//     barrier waits run under the other groups' exponentials.  S = 576: three buffers of 144 keys and three groups (a
+//     group's next S tile is ready when it finishes the current one); S = 144: one buffer, two groups, two CTAs per SM.
+//     The MUFU pipe (one ex2 per score, 16 per clock per SM) and the softmax warps' instruction issue (~8 instructions
+//     per score) are the bounds of this kernel: ~0.6 us per 128 x 144 block each, against ~1.2 us measured;
 //   * softmax across key blocks is the online one with LAZY rescaling: a block adopts the previous blocks' row
 //     maximum unless its own exceeds it by more than 2^8 (probabilities then stay below 256, harmless in fp32 / bf16);
 //     only then are the row's partial O (tcgen05.ld / st) and row sum rescaled - with bounded logits that is rare.  The
@@ -44,7 +46,7 @@ constexpr int AT_MMA_WARPS = 1;                       // one warp (one elected l
                                                       // (and, with 96-key blocks in four buffers, a hang in later-wave CTAs that
                                                       // was not understood); 96-key blocks with a fixed issue order and blocking
                                                       // waits 162 us, with the polling scheduler 146 us; four softmax groups 146 us
-__host__ __device__ constexpr int at_threads(int groups) { return (groups * AT_GROUP_WARPS + AT_MMA_WARPS + AT_LOADER_WARPS) * 32; }   // 352 (2 groups)
+__host__ __device__ constexpr int at_threads(int groups) { return (groups * AT_GROUP_WARPS + AT_MMA_WARPS + AT_LOADER_WARPS) * 32; }   // 352 (2 groups), 480 (3 groups)
 constexpr int AT_QTILE = 128;
 constexpr int AT_ROWB = 128;                          // bytes per staged row (64 bf16)
 constexpr float AT_LAZY = 8.0f;                       // rescale only when the maximum grows by more than 2^8
@@ -627,12 +629,19 @@ int launch_attention_tc(const bf16* qkv, bf16* out, int groups, int seq, int hea
                         cudaStream_t s) {
     if (groups <= 0) return 0;
     if (seq == 576 && rot_pairs == 16) {
-        // GTAV_ATTN_KB=96 (A/B measurements): 6 key blocks per tile in 4 S buffers instead of 3 blocks of 192 keys in 2
-        // (measured 146 us against 128 us for 32 frames: the per-block hand-offs cost more than the extra buffers save)
+        // Default: 4 key blocks of 144 keys per query tile in THREE S buffers, one softmax warpgroup per buffer (480 threads):
+        // a group's next S tile is computed while it works on the current one, instead of waiting for its own P V product to
+        // release one of two buffers.  32 frames: 122.8 us against 131.8 us for 3 blocks of 192 keys in 2 buffers with 2
+        // groups (GTAV_ATTN_KB=192); 6 blocks of 96 keys in 4 buffers: 146 us with 2 groups (GTAV_ATTN_KB=96), 146 us with 4
+        // (964) - the per-block hand-offs cost more than the extra buffers save.  (144 keys x 3 buffers with TWO groups fails
+        // with a launch error that was not tracked down; a buffer count that is a multiple of the group count is the
+        // supported arrangement.)
         const char* e = getenv("GTAV_ATTN_KB");
-        if (e != nullptr && atoi(e) == 96) return launch_tc<576, 96, 4, 512, 2, 16>(qkv, out, groups, heads, rot, s);
-        if (e != nullptr && atoi(e) == 964) return launch_tc<576, 96, 4, 512, 4, 16>(qkv, out, groups, heads, rot, s);
-        return launch_tc<576, 192, 2, 512, 2, 16>(qkv, out, groups, heads, rot, s);
+        const int kb = e != nullptr ? atoi(e) : 0;
+        if (kb == 96) return launch_tc<576, 96, 4, 512, 2, 16>(qkv, out, groups, heads, rot, s);
+        if (kb == 964) return launch_tc<576, 96, 4, 512, 4, 16>(qkv, out, groups, heads, rot, s);
+        if (kb == 192) return launch_tc<576, 192, 2, 512, 2, 16>(qkv, out, groups, heads, rot, s);
+        return launch_tc<576, 144, 3, 512, 3, 16>(qkv, out, groups, heads, rot, s);
     }
     // S = 144: one S buffer and one O buffer in 256 TMEM columns, 72 KB of shared memory -> two CTAs per SM hide each other's
     // staging and hand-off latencies (one CTA has only two (tile, block) steps to pipeline)

@@ -509,9 +509,12 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 8; ++i) __stcg(mine + static_cast<size_t>(c + 8 * j + i) * 128, __uint_as_float(v[j][i]));
         }
-        // release: partial stores ordered before the arrival below (fence + CTA barrier + relaxed atomic); the
-        // acq_rel fence is lighter than __threadfence()'s sequentially-consistent one
+        // release: partial stores ordered before the arrival below - CTA barrier, then ONE gpu-scope fence by the arriving
+        // thread (cumulative over the barrier, the grid-sync idiom), then the relaxed atomic.  GTAV_SK_FENCE_ALL: every
+        // thread fences before the barrier instead (the former arrangement), kept for A/B measurement.
+#ifdef GTAV_SK_FENCE_ALL
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
         tcgen05_fence_before();
         __syncthreads();
         if (warp == 2) {                           // the accumulator has been read by everyone: give the TMEM back now,
@@ -519,6 +522,9 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             tmem_dealloc(tmem_base, tmem_cols);
         }
         if (threadIdx.x == 128) {
+#ifndef GTAV_SK_FENCE_ALL
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
             SK_STAMP(5);                                                       // partials written + fenced
             skinny_rendezvous(meet, meet_n, sense0);
         }

@@ -333,6 +333,11 @@ int gemm_prepare(GemmOp* op, const bf16* A, int lda, const bf16* W, int ldw, con
             const double c = static_cast<double>((tiles + num_sms() - 1) / num_sms()) * cost[i];
             if (c < best - 1e-9) { best = c; bn = cand[i]; }
         }
+        // One round of 256-wide tiles (M <= 1152 at N = 3072 / 4096): two rounds of 128-wide tiles are faster - the first
+        // round's epilogue runs under the second round's mainloop and each tile's prologue / epilogue is half as long.
+        // In-graph, scripts/sweep_gemm_tiles.py --graph: fc1 at M = 1152 / 720 / 576 14.45 / 13.96 / 14.19 -> 13.37 / 12.78 /
+        // 12.53 us, to_qkv at M = 1152 12.73 -> 12.04 us.
+        if (bn == 256 && m_tiles * ((p.N + 255) / 256) <= num_sms()) bn = 128;
     }
     if (bn != 64 && bn != 128 && bn != 256) {
         set_error("gemm: tile width %d not in {64,128,256}", bn);
