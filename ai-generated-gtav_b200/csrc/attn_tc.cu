@@ -339,12 +339,17 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
         for (int n = grp; n < C::NBLK; n += G) {
             const int t = n / C::NKB, j = n - t * C::NKB;
             const uint32_t k = n % NBUF, u = n / NBUF;                   // S buffer and how often it has been used before
-            // A parity wait only tells the current phase from the previous one.  When the number of S buffers is not a
-            // multiple of the number of groups the previous use of buffer k belonged to ANOTHER group, so this group has not
-            // seen that phase complete: go
-            // through it first (it normally has completed long ago), or a wait for phase u posted while the barrier is
-            // still in phase u - 1 returns at once (NBUF = 1: group 1 polls S_FULL[0] from the start of the kernel).
-            if ((NBUF % G) != 0 && u > 0) mbar_wait(&bars[B_SFULL + k], (u - 1) & 1);
+            // A parity wait only tells the current phase from the previous one, so before waiting for phase u of S_FULL[k] the
+            // group must know that phase u - 1 (the buffer's previous use, block n - NBUF) has completed.
+            //  * G < NBUF: it does - the group's own previous block n - G came later in the tensor pipe's in-order sequence
+            //    than block n - NBUF, and the group has consumed it.  (An explicit wait for phase u - 1 would be WRONG here:
+            //    S(n) may already be complete - the other groups run ahead through the spare buffers - and a wait for parity
+            //    u - 1 = parity u + 1 then blocks on the phase this very group has to enable: the scheduler stall of the
+            //    144-key / 3-buffer / 2-group form.)
+            //  * NBUF a multiple of G: the previous use was this group's own block.
+            //  * otherwise (NBUF = 1, G = 2: two blocks in all): go through phase u - 1 first; S(n) cannot be complete yet,
+            //    it needs the P V product of block n - NBUF >= n - G + 1, i.e. of a block not older than this group's last.
+            if (G >= NBUF && (NBUF % G) != 0 && u > 0) mbar_wait(&bars[B_SFULL + k], (u - 1) & 1);
             mbar_wait(&bars[B_SFULL + k], u & 1);
             tcgen05_fence_after();
             if (tr) AT_STAMP(tr_role);                                   // S full
@@ -633,14 +638,15 @@ int launch_attention_tc(const bf16* qkv, bf16* out, int groups, int seq, int hea
         // a group's next S tile is computed while it works on the current one, instead of waiting for its own P V product to
         // release one of two buffers.  32 frames: 122.8 us against 131.8 us for 3 blocks of 192 keys in 2 buffers with 2
         // groups (GTAV_ATTN_KB=192); 6 blocks of 96 keys in 4 buffers: 146 us with 2 groups (GTAV_ATTN_KB=96), 146 us with 4
-        // (964) - the per-block hand-offs cost more than the extra buffers save.  (144 keys x 3 buffers with TWO groups fails
-        // with a launch error that was not tracked down; a buffer count that is a multiple of the group count is the
-        // supported arrangement.)
+        // (964) - the per-block hand-offs cost more than the extra buffers save.  144 keys x 3 buffers with TWO groups
+        // (GTAV_ATTN_KB=1442; a spare buffer per group, so no group ever waits for its own P V product): 132 us - the third
+        // buffer alone buys nothing, the third group's instruction issue does.
         const char* e = getenv("GTAV_ATTN_KB");
         const int kb = e != nullptr ? atoi(e) : 0;
         if (kb == 96) return launch_tc<576, 96, 4, 512, 2, 16>(qkv, out, groups, heads, rot, s);
         if (kb == 964) return launch_tc<576, 96, 4, 512, 4, 16>(qkv, out, groups, heads, rot, s);
         if (kb == 192) return launch_tc<576, 192, 2, 512, 2, 16>(qkv, out, groups, heads, rot, s);
+        if (kb == 1442) return launch_tc<576, 144, 3, 512, 2, 16>(qkv, out, groups, heads, rot, s);
         return launch_tc<576, 144, 3, 512, 3, 16>(qkv, out, groups, heads, rot, s);
     }
     // S = 144: one S buffer and one O buffer in 256 TMEM columns, 72 KB of shared memory -> two CTAs per SM hide each other's
