@@ -182,7 +182,7 @@ struct AttnCfg {
 // i from phase i + 2) exists once per S buffer / O buffer / query slot, so that the producer's next arrival depends on
 // the consumer having gone through.
 enum { B_QFULL = 0, B_QFREE = 2, B_SFULL = 4, B_SFREE = 8, B_PREADY = 12, B_OFULL = 16, B_OFREE = 18, B_MREADY = 20,
-       B_LREADY = 21, B_DBG = 22, B_COUNT = 23 };
+       B_LREADY = 24, B_DBG = 25, B_COUNT = 26 };   // M_READY: one barrier per softmax group (up to 4)
 
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {       // non-blocking probe (try_wait may suspend)
     uint32_t ok;
@@ -244,7 +244,7 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
             mbar_init(&bars[B_SFREE + i], 1);
             mbar_init(&bars[B_PREADY + i], AT_GROUP_WARPS * 32);
         }
-        mbar_init(&bars[B_MREADY], AT_GROUP_WARPS * 32);
+        for (int i = 0; i < 4; ++i) mbar_init(&bars[B_MREADY + i], AT_GROUP_WARPS * 32);
         mbar_init(&bars[B_LREADY], (C::L_PUBLISHERS > 0 ? C::L_PUBLISHERS : 1) * AT_GROUP_WARPS * 32);
         mbar_init(&bars[B_DBG], 1);
         fence_barrier_init();
@@ -390,14 +390,27 @@ attn_tc_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int heads, 
             if (tr) AT_STAMP(tr_role);                                   // block maximum known
             // ---- the maximum this row is expressed in: the previous block's, unless this block's exceeds it by > 2^8
             float m_use = bm, o_scale = 1.0f;
-            if (n > 0) mbar_wait(&bars[B_MREADY], (n - 1) & 1);          // (every block waits: keeps the phases in step)
+            // The row maximum travels from block n - 1 to block n through M_READY[(n - 1) % G]: one barrier per PRODUCING
+            // group, so that its only waiter - the next group - sees every phase of it.  With a single barrier for all blocks
+            // a group of G >= 3 skipped two phases between its waits, and a parity wait posted while the barrier was still
+            // two phases behind returned at once: stale maximum, arrivals in the wrong phase and, eventually, a stalled
+            // scheduler (seen once in a VAE decode, never in the unit tests).
+#ifdef GTAV_ATTN_SINGLE_MREADY                         // the former single-barrier chain, kept to show that the stress test catches it
+            if (n > 0) mbar_wait(&bars[B_MREADY], (n - 1) & 1);
+#else
+            if (n > 0) mbar_wait(&bars[B_MREADY + (n - 1) % G], ((n - 1) / G) & 1);
+#endif
             if (j > 0) {
                 const float m_prev = sM[row];
                 if ((bm - m_prev) * sl2 > AT_LAZY) o_scale = ex2_approx((m_prev - bm) * sl2);
                 else m_use = m_prev;
             }
             sM[row] = m_use;
+#ifdef GTAV_ATTN_SINGLE_MREADY
             mbar_arrive(&bars[B_MREADY]);
+#else
+            mbar_arrive(&bars[B_MREADY + n % G]);
+#endif
             if (tr) AT_STAMP(tr_role);                                   // row maximum handed on
             if (j < G) {                                                 // this group's first block of the tile (its blocks are G apart)
                 l = 0.f;

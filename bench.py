@@ -266,10 +266,10 @@ def skinny_roofline(dit, B, pk):
                 kernel="gemm_skinny_kernel (tcgen05 weight-streaming GEMM, 128 launches per last-frame DiT step)",
                 algorithmic_mb_per_launch=round(gb * 1e3 / (4 * len(halves)), 3), us_per_launch=round(ms * 1e3 / (4 * len(halves)), 3),
                 gemm_ms_per_last_frame_step=round(ms, 4), peak_source=f"{pk['src']} HBM copy bandwidth",
-                note="latency-bound, not bandwidth-bound: a launch is a chain of L2 round trips (CTA entry, operand slab 1.5 us, "
-                     "MMA 0.8, split-K partials out 2.1, rendezvous 0.7-1.3, reduce + fused LayerNorm / temporal attention 1.8-2.7; "
-                     "profiles/r01/skinny_in_step_trace_v8.txt); its DRAM traffic equals the algorithmic bytes "
-                     "(profiles/r01/roofline_traffic.json)")
+                note="latency-bound, not bandwidth-bound: a launch is a chain of L2 round trips (CTA entry + set-up 0.35 us, operand "
+                     "slabs 0.8-1.4, MMA 0.8, split-K partials out 1.9, rendezvous 0.7-0.9, reduce + fused LayerNorm / temporal "
+                     "attention 1.5-2.0, next kernel's CTAs 0.6-0.9 later; profiles/r02/skinny_in_step_trace_b.txt); its DRAM "
+                     "traffic equals the algorithmic bytes (profiles/r02/roofline_traffic.json)")
 
 
 def cpu_c1_run(init="initB", dit_steps_budget=None):

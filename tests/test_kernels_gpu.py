@@ -216,6 +216,45 @@ def test_attention_seq(lib, monkeypatch, seq, pairs, groups, impl):
     assert float(err.max()) < 2e-2 and float(err.mean()) < 2e-3, (float(err.max()), float(err.mean()))
 
 
+@pytest.mark.parametrize("kb", ["", "192", "1442", "964"])
+def test_attention_seq_rescale_stress(lib, monkeypatch, kb):
+    """The tcgen05 attention under the conditions that once stalled it in a VAE decode: logits whose block maximum jumps by
+    > 2^8 from key block to key block in half of the heads (the rare rescale path of the lazy online softmax runs in every
+    tile there, never in the other heads, so the softmax groups of a CTA drift apart), many CTAs, many launches.  Every
+    launch must give the same bits, and those must match the fp32 softmax.  kb: the S-buffer / group arrangement
+    (default 3 x 144 keys x 3 groups; 192: 2 x 192 x 2; 1442: 3 x 144 x 2; 964: 4 x 96 x 4)."""
+    monkeypatch.setenv("GTAV_ATTN", "tc")
+    if kb:
+        monkeypatch.setenv("GTAV_ATTN_KB", kb)
+    N = _N()
+    H, d, seq, pairs, groups = 16, 64, 576, 16, 40
+    g = torch.Generator(device="cuda").manual_seed(7)
+    qkv = (torch.randn((groups, seq, 3, H, d), device="cuda", generator=g) * 0.5)
+    pos = torch.arange(seq, device="cuda").float()
+    step = torch.where(torch.arange(H, device="cuda") % 2 == 0, 1.0, -1.0)           # rising / falling block maxima per head
+    c = 9.0 * torch.floor(pos / 96.0)[:, None] * step[None, :]                      # [seq, H]: +-9 logits per 96 keys
+    qkv[:, :, 0, :, 40] = 8.0                                                        # q . k / 8 = c(key) (+ noise); dim 40 is not rotated
+    qkv[:, :, 1, :, 40] = c[None]
+    qkv = qkv.reshape(groups * seq, 3 * H * d).to(torch.bfloat16)
+    ang = torch.rand((seq, pairs), device="cuda", generator=g) * 20 - 10
+    rot = _rot_table(ang)
+    outs = []
+    for _ in range(12):
+        out = torch.empty((groups * seq, H * d), dtype=torch.bfloat16, device="cuda")
+        N.check(lib.gtav_attention_seq(qkv.data_ptr(), out.data_ptr(), groups, seq, H, rot.data_ptr(), pairs,
+                                       N.current_stream()), "attention_seq")
+        outs.append(out)
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    q, k, v = [z.float().reshape(groups, seq, H, d).permute(0, 2, 1, 3) for z in qkv.chunk(3, dim=-1)]
+    q, k = _rotate(q, ang), _rotate(k, ang)
+    p = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1)
+    ref = (p @ v).permute(0, 2, 1, 3).reshape(groups * seq, H * d)
+    err = (outs[0].float() - ref).abs()
+    assert float(err.max()) < 2e-2 and float(err.mean()) < 2e-3, (float(err.max()), float(err.mean()))
+
+
 @pytest.mark.parametrize("B,T", [(1, 5), (2, 3), (1, 1)])
 def test_attention_temporal(lib, B, T):
     N = _N()
