@@ -15,13 +15,14 @@
 //     alternatives for the operand loads, all slower in the real step (profiles/r01/bench_engine_v6.log): 2 / 4 boxes
 //     per operand from different warps (+1 % / +8 % step time: every extra TMA instruction costs), the token slab
 //     through cp.async with a software swizzle next to the TMA-loaded weights (+6 %);
-//   * partial accumulators go to an fp32 workspace (L2), the S CTAs of a row block meet on a
+//   * partial accumulators go to an fp32 workspace (L2; released by one gpu-scope fence of the arriving thread after the
+//     CTA barrier), the S CTAs of a row block meet on a
 //     counter, and each reduces + runs the fused epilogue for its 1/S share of the tokens, summing
 //     the partials in split order (deterministic);
 //   * optionally the reduce is done per token row by every CTA (plus reduce-only CTAs up to one per token), which lets
 //     the row-wise kernel that would follow - LayerNorm + modulate, or the last-frame temporal attention - run inside
 //     it; everything those need besides the partial sums is loaded BEFORE the rendezvous.
-// Warp roles (256 threads): 0 = W producer, 1 = A producer, 2 = TMEM allocator + MMA issuer; all 8 warps drain the
+// Warp roles (256 threads): 0 = W producer, 1 = A producer, 2 = TMEM allocator + MMA issue (warp-uniform loop, elect.sync); all 8 warps drain the
 // accumulator (one TMEM lane quadrant each, half of the columns) and reduce.  (An optional L2 prefetch of the next GEMM's
 // weights, issued once the accumulator is complete, is off by default: GemmParams::prefetch, see dit_engine.cu.)
 #include "attn_temporal_core.cuh"

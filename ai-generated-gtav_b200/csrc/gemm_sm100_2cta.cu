@@ -28,8 +28,12 @@ namespace gtav {
 static constexpr int G2_BM = 128;              // rows per CTA (256 per pair)
 static constexpr int G2_BN = 256;
 static constexpr int G2_BK = 64;
-static constexpr int G2_KC = 2;                // 64-wide K chunks per stage
-static constexpr int G2_STAGES = 3;
+#ifndef GTAV_G2_KC                             // (overridable for A/B builds: scripts/ab_define.sh)
+#define GTAV_G2_KC 2
+#define GTAV_G2_STAGES 3
+#endif
+static constexpr int G2_KC = GTAV_G2_KC;       // 64-wide K chunks per stage
+static constexpr int G2_STAGES = GTAV_G2_STAGES;
 static constexpr int G2_THREADS = 416;             // 13 warps: 5 producer / MMA + 8 epilogue
 static constexpr int G2_A_CHUNK = G2_BM * G2_BK * 2;           // 16 KB
 static constexpr int G2_B_CHUNK = (G2_BN / 2) * G2_BK * 2;     // 16 KB: this CTA's half of the weight rows
@@ -140,7 +144,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         pdl_wait();                                   // A is the previous kernel's output
         int s = 0;
         uint32_t ph = 1;
-        for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+        for (int tile = cluster_id; tile < n_tiles && j < G2_KC; tile += n_clusters) {
             const int m_row = ((tile / n_tiles_n) * 2 + static_cast<int>(rank)) * G2_BM;
             for (int ks = 0; ks < num_ks; ++ks) {
                 mbar_wait(&empty_bar[s], ph);
@@ -156,7 +160,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int j = warp == 6 ? 0 : 1;
         int s = 0;
         uint32_t ph = 1;
-        for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+        for (int tile = cluster_id; tile < n_tiles && j < G2_KC; tile += n_clusters) {
             const int n_row = (tile % n_tiles_n) * G2_BN + static_cast<int>(rank) * (G2_BN / 2);
             for (int ks = 0; ks < num_ks; ++ks) {
                 mbar_wait(&empty_bar[s], ph);
