@@ -6,16 +6,17 @@
 // round to bf16 exactly where the reference's autocast graph does.
 //
 // Structure (persistent CTAs over 128 x BN output tiles, double-buffered TMEM accumulator, 416 threads):
-//   warps 0,7: TMA producers of A - a stage is KC = 2 consecutive 64-wide K chunks of 128 rows, one box per thread
+//   warps 0,7: TMA producers of A - a stage is KC = 2 consecutive 64-wide K chunks of 128 rows, one box per warp
 //   warps 6,8: TMA producers of W - the same for BN weight rows; they run ahead of the previous kernel (PDL): weights
 //              do not depend on it
-//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1)
+//   warp 1   : TMEM allocator + tcgen05.mma issue (UMMA 128 x BN x 16, cta_group::1): warp-uniform loops, elect.sync
+//              picks the issuing lane
 //   warps 2-5, 9-12: epilogue - tcgen05.ld 32x32b from their TMEM lane quadrant (two warps per quadrant, half of the
 //              tile's columns each), fused math, 16-byte stores.  Eight warps: with four, a K = 1024 tile's GELU
 //              epilogue outlasts its mainloop (measured on the CTA-pair kernel: 668 -> 968 TFLOP/s on fc1)
 // smem full/empty mbarrier ring between the producers and the issuer; tcgen05.commit frees slots and signals
 // the epilogue.  Out-of-range rows / columns / K are zero-filled by TMA and masked in the epilogue.
-// Why four producer threads: measured on B200 (scripts/probe_tma*.cu, scripts/probe_mcast.cu, profiles/r01), one
+// Why four producer warps: measured on B200 (scripts/probe_tma*.cu, scripts/probe_mcast.cu, profiles/r01), one
 // thread gets a bulk copy accepted only every ~0.4 us whatever its size, so a stage issued by one thread caps a CTA
 // at ~45 GB/s (5x short of what a 128x128 tile needs) and two threads with 32 KB boxes at ~160 GB/s; copies from
 // different threads proceed in parallel, and a 128 x 256 tile at full tensor rate needs ~175 GB/s.
@@ -193,13 +194,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             mbar_wait(&tfull_bar[acc], (local >> 1) & 1);
             tcgen05_fence_after();
+            // Two register buffers: the tcgen05.ld of the next 32 columns is in flight while the current ones go through the
+            // epilogue math and their stores (context pass 1.88 -> 1.83 ms, dense B = 1 step 1.89 -> 1.87 ms).  Not for the
+            // erf GELU, whose two inlined epilogue copies cost more than the overlap gains (see gemm_sm100_2cta.cu).
+            {
+                const uint32_t tbase = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+                if (EPI == EPI_BIAS_GELU_ERF) {
 #pragma unroll 1
-            for (int c = c_lo; c < c_hi; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
-                tmem_ld_wait();
-                const int col0 = n_blk * BN + c * 32;
-                if (row < p.M && col0 < p.N) epilogue_chunk<EPI>(p, row, col0, v, gate_row);
+                    for (int c = c_lo; c < c_hi; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(tbase + c * 32, v);
+                        tmem_ld_wait();
+                        const int col0 = n_blk * BN + c * 32;
+                        if (row < p.M && col0 < p.N) epilogue_chunk<EPI>(p, row, col0, v, gate_row);
+                    }
+                } else {
+                    uint32_t va[32], vb[32];
+                    tmem_ld_32x32(tbase + c_lo * 32, va);
+#pragma unroll 1
+                    for (int c = c_lo; c < c_hi; c += 2) {
+                        tmem_ld_wait();
+                        if (c + 1 < c_hi) tmem_ld_32x32(tbase + (c + 1) * 32, vb);
+                        int col0 = n_blk * BN + c * 32;
+                        if (row < p.M && col0 < p.N) epilogue_chunk<EPI>(p, row, col0, va, gate_row);
+                        if (c + 1 < c_hi) {
+                            tmem_ld_wait();
+                            if (c + 2 < c_hi) tmem_ld_32x32(tbase + (c + 2) * 32, va);
+                            col0 += 32;
+                            if (row < p.M && col0 < p.N) epilogue_chunk<EPI>(p, row, col0, vb, gate_row);
+                        }
+                    }
+                }
             }
             tcgen05_fence_before();
             __syncwarp();
