@@ -364,6 +364,14 @@ int gemm_prepare(GemmOp* op, const bf16* A, int lda, const bf16* W, int ldw, con
         // 12.53 us, to_qkv at M = 1152 12.73 -> 12.04 us.
         if (bn == 256 && m_tiles * ((p.N + 255) / 256) <= num_sms()) bn = 128;
     }
+    // Few tiles and a long K (fc2 at M <= 1152): the K-serial mainloop dominates - two CTAs per 128 x 128 tile, half of K
+    // each (gemm_sm100_splitk.cu).  GTAV_GEMM_SPLITK=0 / 1 forces the choice (1: whenever eligible).
+    op->split_k = 0;
+    if (bn_override == 0 && gemm_splitk_eligible(p.M, p.N, p.K, num_sms())) {
+        const char* e = getenv("GTAV_GEMM_SPLITK");
+        op->split_k = e != nullptr ? (e[0] == '1') : 1;
+        if (op->split_k) bn = 128;
+    }
     if (bn != 64 && bn != 128 && bn != 256) {
         set_error("gemm: tile width %d not in {64,128,256}", bn);
         return -1;
@@ -379,7 +387,7 @@ int gemm_prepare(GemmOp* op, const bf16* A, int lda, const bf16* W, int ldw, con
     // CTA pairs (gemm_sm100_2cta.cu) where the shape allows and the GEMM is large enough to be ingest-bound on one
     // SM.  GTAV_GEMM_2CTA=0 / 1 forces the choice (1: whenever eligible).
     op->two_cta = 0;
-    if (bn_override == 0 && gemm2_eligible(p.M, p.N, p.K)) {
+    if (bn_override == 0 && !op->split_k && gemm2_eligible(p.M, p.N, p.K)) {
         const char* e = getenv("GTAV_GEMM_2CTA");
         // same cost model for the CTA pair: a 256 x 256 tile pair on two SMs is MMA-bound (130 cycles per K = 16 step:
         // each SM ingests a third less), rounds over the num_sms / 2 clusters.  E.g. (scripts/bench_2cta.py) M = 1152
@@ -439,6 +447,7 @@ static int launch_epi(const GemmOp* op, cudaStream_t stream) {
 }
 
 int gemm_run(const GemmOp* op, cudaStream_t stream) {
+    if (op->split_k) return gemm_splitk_run(op, stream);
     if (op->two_cta) return gemm2_run(op, stream);
     switch (op->epi) {
         case EPI_STORE: return launch_epi<EPI_STORE>(op, stream);

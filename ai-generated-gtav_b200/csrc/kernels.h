@@ -71,6 +71,7 @@ struct GemmOp {
     CUtensorMap tmA, tmB;
     CUtensorMap tmB2;   // CTA-pair kernel (gemm_sm100_2cta.cu): boxes of 128 weight rows (each CTA loads half of a 256-wide tile)
     int two_cta;        // 1: run the cta_group::2 kernel
+    int split_k;        // 1: run the split-K pair kernel (gemm_sm100_splitk.cu): few tiles, long K
     GemmParams p;
     int bn;      // tile width chosen at prepare time (64 / 128 / 256)
     int kc;      // 64-wide K chunks per TMA instruction / pipeline stage (1: 2-D maps, any K; 2: 3-D maps, K % 64 == 0)
@@ -85,6 +86,10 @@ int gemm_run(const GemmOp* op, cudaStream_t stream);
 // CTA-pair variant (tcgen05.mma.cta_group::2, 256 x 256 tiles): M >= 256, N % 256 == 0, K % 128 == 0
 bool gemm2_eligible(int M, int N, int K);
 int gemm2_run(const GemmOp* op, cudaStream_t stream);
+// Split-K variant (two CTAs of a cluster share a 128 x 128 tile, half of K each, DSMEM reduce): K >= 2048, K % 256 == 0,
+// N % 128 == 0 and 2 x tiles <= SMs
+bool gemm_splitk_eligible(int M, int N, int K, int sms);
+int gemm_splitk_run(const GemmOp* op, cudaStream_t stream);
 
 // [rows, cols] bf16 row-major (leading dimension ld) viewed as [64 | rows | cols/64]: boxes of
 // box_rows x (box_chunks * 64) land in shared memory as box_chunks consecutive 128-byte-swizzled

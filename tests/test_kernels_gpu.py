@@ -23,11 +23,12 @@ def r16(x):
     return x.to(torch.bfloat16).float()
 
 
-def run_gemm(lib, A, W, epi, bias=None, res=None, gate=None, frame_row=None, rows_per_frame=1, bn=0, N_out=None):
+def run_gemm(lib, A, W, epi, bias=None, res=None, gate=None, frame_row=None, rows_per_frame=1, bn=0, N_out=None, out=None):
     N = _N()
     M, K = A.shape
     Nn = W.shape[0] if N_out is None else N_out
-    out = torch.zeros((M, Nn), dtype=torch.bfloat16, device="cuda")
+    if out is None:
+        out = torch.zeros((M, Nn), dtype=torch.bfloat16, device="cuda")
     N.check(lib.gtav_gemm_bf16(A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), out.data_ptr(), out.stride(0), M, Nn, K,
                                epi, N.ptr(bias), N.ptr(res), 0 if res is None else res.stride(0), N.ptr(gate),
                                0 if gate is None else gate.stride(0), N.ptr(frame_row), rows_per_frame, bn,
@@ -419,6 +420,39 @@ def test_gemm_cta_pair_equals_single_cta(lib, monkeypatch, M, N, K):
         outs[mode] = (run_gemm(lib, A, W, Nmod.EPI_STORE), run_gemm(lib, A, W, Nmod.EPI_BIAS_GELU_TANH, bias=bias))
     close_bf16(outs["1"][0], A.float() @ W.float().t())
     assert torch.equal(outs["0"][0], outs["1"][0]) and torch.equal(outs["0"][1], outs["1"][1])
+
+
+@pytest.mark.parametrize("M,N,K", [(1152, 1024, 4096), (720, 1024, 4096), (144, 1024, 2048), (1000, 256, 2048), (576, 1024, 4096)])
+def test_gemm_split_k_pair(lib, monkeypatch, M, N, K):
+    """Split-K over the two CTAs of a cluster with the DSMEM reduce (gemm_sm100_splitk.cu; chosen for few tiles and K >= 2048,
+    i.e. fc2 at M <= 1152): plain store, GELU and the gated in-place residual against the fp32 product, and within the
+    rounding of the summation order of the single-CTA kernel (GTAV_GEMM_SPLITK=0)."""
+    Nmod = _N()
+    S = 144
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + 1)
+    A = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
+    W = (torch.randn((N, K), device="cuda", generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = (torch.randn((N,), device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    res = torch.randn((M, N), device="cuda", generator=g).to(torch.bfloat16)
+    frames = (M + S - 1) // S
+    gate = torch.randn((frames + 1, N), device="cuda", generator=g).to(torch.bfloat16)
+    frame_row = torch.arange(frames, 0, -1, dtype=torch.int32, device="cuda")
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("GTAV_GEMM_SPLITK", mode)
+        h = res.clone()
+        run_gemm(lib, A, W, Nmod.EPI_BIAS_GATE_RES, bias=bias, res=h, gate=gate, frame_row=frame_row, rows_per_frame=S, out=h)
+        outs[mode] = (run_gemm(lib, A, W, Nmod.EPI_STORE), run_gemm(lib, A, W, Nmod.EPI_BIAS_GELU_TANH, bias=bias), h)
+    prod = A.float() @ W.float().t()
+    y = r16(prod + bias.float())
+    grow = gate[frame_row.long()].float().repeat_interleave(S, dim=0)[:M]
+    close_bf16(outs["1"][0], prod)
+    # (y itself may sit one bf16 ulp away from the fp32 product's rounding at K = 4096; the gate multiplies that)
+    close_bf16(outs["1"][1], torch.nn.functional.gelu(y, approximate="tanh"), ulps=3.0)
+    close_bf16(outs["1"][2], res.float() + r16(grow * y), ulps=4.0, mag=res.float().abs() + (grow * y).abs())
+    for a, b in zip(outs["1"], outs["0"]):
+        d = (a.float() - b.float()).abs()
+        assert float(d.max()) <= 0.07 and float((d > 0).float().mean()) < 0.05, (float(d.max()), float((d > 0).float().mean()))
 
 
 def test_gemm_cta_pair_gated_residual_in_place(lib, monkeypatch):

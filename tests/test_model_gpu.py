@@ -80,8 +80,9 @@ def test_dit_forward_bf16_input_and_replan():
 
 LAST_FRAME_MODES = {
     # name: (GTAV_SKINNY, max-abs bound vs the dense window)
-    "tiled": ("0", 0.0),        # same kernels, same arithmetic per row: bit-identical
-    "skinny": ("1", 2e-2),      # weight-streaming GEMM: fp32 summation order inside the K splits differs
+    "tiled": ("0", "0", 0.0),       # same full-K tiled kernels, same arithmetic per row: bit-identical
+    "tiled_splitk": ("0", "1", 2e-2),  # fc2 of the small pass on the split-K pair kernel: (k < K/2) + (k >= K/2) summation
+    "skinny": ("1", "1", 2e-2),     # weight-streaming GEMM: fp32 summation order inside the K splits differs
 }
 
 
@@ -89,8 +90,10 @@ LAST_FRAME_MODES = {
 def test_dit_last_frame_split_equals_dense(monkeypatch, mode):
     """Context pass + last-frame-only pass (the sampler's frame cache) == the last frame of the dense forward."""
     from gtav_b200.model.dit import DiT
-    skinny, bound = LAST_FRAME_MODES[mode]
+    skinny, splitk, bound = LAST_FRAME_MODES[mode]
     monkeypatch.setenv("GTAV_SKINNY", skinny)
+    if splitk == "0":
+        monkeypatch.setenv("GTAV_GEMM_SPLITK", "0")
     sd = make_dit_state(DiTConfig(depth=2), seed=0)
     model = DiT(depth=2)
     model.load_state_dict(sd, strict=True)
