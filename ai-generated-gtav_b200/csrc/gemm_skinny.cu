@@ -239,8 +239,9 @@ __device__ __forceinline__ void skinny_reduce_any(const GemmParams& g, const flo
 // griddepcontrol.wait: by the time the rendezvous completes they are in registers / shared memory.
 //
 // SK_FUSE_LN (N = 1024, gated-residual epilogue: to_out and fc2 of reference model/dit.py:205-224): warp w sums the
-// partials of row block w, the new residual-stream row goes to g.out and, as bf16, to shared memory; warp 0 then
-// runs the NEXT LayerNorm + modulate on it with ln_rows_kernel's own code (same bits as the stand-alone kernel).
+// partials of row block w and writes its part of the new residual-stream row to g.out; the 8 warps then run the NEXT
+// LayerNorm + modulate on the row together, each on its own 128 features, exchanging only the 8 segment sums of the
+// two statistics passes through shared memory (ln_row.cuh: same bits as the stand-alone one-warp-per-row kernel).
 // smod: 2 KB shift | 2 KB scale of the token's frame, filled cooperatively (thread i: 16 bytes).
 __device__ __forceinline__ Epi4Ops skinny_ln_preload(const SkinnyParams& p, int tok, int warp, uint8_t* smod) {
     const GemmParams& g = p.g;
@@ -265,6 +266,7 @@ __device__ __forceinline__ void skinny_reduce_ln(const SkinnyParams& p, int S, i
     const int n = warp * 128 + 4 * lane;
     const float* base = p.ws + static_cast<size_t>(warp) * S * total * 128 + 4 * lane;
     const size_t stride = static_cast<size_t>(total) * 128;
+    float* sred = reinterpret_cast<float*>(srow);            // [2][8] segment sums (values, then squared deviations)
 #pragma unroll 1
     for (int tok = blockIdx.x; tok < total; tok += gridDim.x) {
         const float* p0 = base + static_cast<size_t>(tok) * 128;
@@ -276,25 +278,26 @@ __device__ __forceinline__ void skinny_reduce_ln(const SkinnyParams& p, int S, i
         }
         const uint2 o = skinny_epi4<EPI_BIAS_GATE_RES>(acc, e);
         *reinterpret_cast<uint2*>(g.out + static_cast<size_t>(tok) * g.ldo + n) = o;
-        *reinterpret_cast<uint2*>(srow + n * 2) = o;
-        __syncthreads();                       // the row (and, first time round, the preloaded shift / scale) is in smem
-        if (warp == 0) {
-            uint4 xu[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) xu[c] = *reinterpret_cast<const uint4*>(srow + (c * 256 + lane * 8) * 2);
-            float x[4][8];
-            float mean, rstd;
-            ln_row_stats<4>(xu, x, mean, rstd);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const uint4 sh = *reinterpret_cast<const uint4*>(smod + (c * 256 + lane * 8) * 2);
-                const uint4 sc = *reinterpret_cast<const uint4*>(smod + 2048 + (c * 256 + lane * 8) * 2);
-                *reinterpret_cast<uint4*>(f.ln_out + static_cast<size_t>(tok) * 1024 + c * 256 + lane * 8) =
-                    ln_modulate_slice(x[c], mean, rstd, sh, sc);
-            }
-        }
+        // LayerNorm of the row held by the 8 warps (128 features each, one quad per lane) in the summation order ln_row.cuh
+        // defines on exactly this layout - the stand-alone kernel reproduces it with one warp.  Two CTA barriers for the two
+        // passes of the statistics instead of a round trip of the whole row through shared memory and one warp's serial work.
+        const float2 x01 = unpack_bf16x2(o.x), x23 = unpack_bf16x2(o.y);
+        const float x[4] = {x01.x, x01.y, x23.x, x23.y};
+        const float s1 = warp_sum(ln_quad_sum(x[0], x[1], x[2], x[3]));
+        if (lane == 0) sred[warp] = s1;
+        __syncthreads();                       // (first time round this also publishes the preloaded shift / scale)
+        const float mean = __fmul_rn(ln_combine8(sred[0], sred[1], sred[2], sred[3], sred[4], sred[5], sred[6], sred[7]), 1.0f / 1024);
+        const float s2 = warp_sum(ln_quad_sq(x[0], x[1], x[2], x[3], mean));
+        if (lane == 0) sred[8 + warp] = s2;
         __syncthreads();
-        if (tok + static_cast<int>(gridDim.x) < total) e = skinny_ln_preload(p, tok + gridDim.x, warp, smod);
+        const float rstd = ln_rstd(ln_combine8(sred[8], sred[9], sred[10], sred[11], sred[12], sred[13], sred[14], sred[15]), 1024);
+        const uint2 sh = *reinterpret_cast<const uint2*>(smod + n * 2);
+        const uint2 sc = *reinterpret_cast<const uint2*>(smod + 2048 + n * 2);
+        *reinterpret_cast<uint2*>(f.ln_out + static_cast<size_t>(tok) * 1024 + n) = ln_modulate_quad(x, mean, rstd, sh, sc);
+        if (tok + static_cast<int>(gridDim.x) < total) {
+            __syncthreads();                   // everyone is done with sred / smod before they are rewritten
+            e = skinny_ln_preload(p, tok + gridDim.x, warp, smod);
+        }
     }
 }
 
