@@ -44,8 +44,10 @@ struct gtav_dit_plan_s {
     // workspace slices
     bf16 *xa, *h, *hn, *qkv, *att, *mlp, *yfin, *temb, *aemb, *h1, *cact, *mod;
     bf16* kv_cache;          // [depth][B*(T-1)*tokens][2*hidden]: rotated K and V of the context frames per temporal layer
-    float* sk_ws;            // split-K partial sums of the weight-streaming GEMM / of the persistent step kernel
+    float* sk_ws;            // split-K partial sums of the weight-streaming GEMM: four regions of sk_ws_bytes, one per GEMM
+    size_t sk_ws_bytes;      // kind (to_qkv, to_out, fc1, fc2), so that the tagged exchange sees only its own shape's data
     int* sk_counters;
+    bool sk_out_of_step = false;   // a last-frame pass failed part-way: the tagged exchange's parities no longer line up
     GemmOp g_t0, g_t2, g_ada;
     Shape full, ctx, last;   // all T frames / the T-1 context frames / the last frame only
 };
@@ -82,8 +84,8 @@ void carve(gtav_dit_plan_s* p, void* ws, size_t* total) {
     const size_t ctx_rows = static_cast<size_t>(p->B) * (p->T - 1) * e->tokens;
     p->kv_cache = c.take(static_cast<size_t>(e->cfg.depth) * ctx_rows * 2 * D);
     const int m_last = p->B * e->tokens;
-    size_t ws_bytes = p->B <= 3 ? skinny_workspace_bytes(m_last) : 0;
-    p->sk_ws = reinterpret_cast<float*>(c.take(ws_bytes / sizeof(bf16)));
+    p->sk_ws_bytes = p->B <= 3 ? skinny_workspace_bytes(m_last) : 0;
+    p->sk_ws = reinterpret_cast<float*>(c.take(4 * p->sk_ws_bytes / sizeof(bf16)));
     p->sk_counters = reinterpret_cast<int*>(c.take(1024));      // 512 ints: 4 per rendezvous group (gemm_skinny.cu)
     *total = c.off;
 }
@@ -97,6 +99,12 @@ GemmParams gp(bf16* out, int ldo, const void* bias, int M, int N, int K) {
 
 bool skinny_enabled() {
     const char* e = getenv("GTAV_SKINNY");
+    return !(e != nullptr && e[0] == '0');
+}
+
+// GTAV_SK_TAG=0: the weight-streaming GEMMs' CTAs meet on counters instead of exchanging tagged partial sums (gemm_skinny.cu).
+bool tag_enabled() {
+    const char* e = getenv("GTAV_SK_TAG");
     return !(e != nullptr && e[0] == '0');
 }
 
@@ -176,13 +184,19 @@ int build_shape(gtav_dit_plan_s* p, Shape* sh, int frames, bool allow_skinny) {
         f_qkv.positions = S;
         const bool ta = sh->fuse_tattn && (i & 1);
         if (ta) { pq.out = p->att; pq.ldo = D; }
-        if (sh->sk[0]) rc |= skinny_prepare(&sh->s_qkv[i], p->hn, D, static_cast<const bf16*>(hw.qkv_w), D, pq, EPI_STORE, p->sk_ws, p->sk_counters, so[0], ta ? &f_qkv : nullptr);
+        // Tagged exchange of the split-K partial sums: every GEMM kind has its own workspace region (zeroed at plan creation)
+        // and the 2 * depth launches of a pass alternate the parity on it, 1 first - an even count, so every pass leaves the
+        // region at parity 0 and the next pass, or a replay of the captured graph, starts from the same state.
+        float* ws4[4];
+        for (int k = 0; k < 4; ++k) ws4[k] = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(p->sk_ws) + k * p->sk_ws_bytes);
+        const int tag = tag_enabled() ? (2 | ((i & 1) ^ 1)) : 0;
+        if (sh->sk[0]) { rc |= skinny_prepare(&sh->s_qkv[i], p->hn, D, static_cast<const bf16*>(hw.qkv_w), D, pq, EPI_STORE, ws4[0], p->sk_counters, so[0], ta ? &f_qkv : nullptr); sh->s_qkv[i].tag = tag; }
         else rc |= gemm_prepare(&sh->g_qkv[i], p->hn, D, static_cast<const bf16*>(hw.qkv_w), D, pq, EPI_STORE);
-        if (sh->sk[1]) rc |= skinny_prepare(&sh->s_out[i], p->att, D, static_cast<const bf16*>(hw.out_w), D, po, EPI_BIAS_GATE_RES, p->sk_ws, p->sk_counters, so[1], sh->fuse_ln ? &f_out : nullptr);
+        if (sh->sk[1]) { rc |= skinny_prepare(&sh->s_out[i], p->att, D, static_cast<const bf16*>(hw.out_w), D, po, EPI_BIAS_GATE_RES, ws4[1], p->sk_counters, so[1], sh->fuse_ln ? &f_out : nullptr); sh->s_out[i].tag = tag; }
         else rc |= gemm_prepare(&sh->g_out[i], p->att, D, static_cast<const bf16*>(hw.out_w), D, po, EPI_BIAS_GATE_RES);
-        if (sh->sk[2]) rc |= skinny_prepare(&sh->s_fc1[i], p->hn, D, static_cast<const bf16*>(hw.fc1_w), D, p1, EPI_BIAS_GELU_TANH, p->sk_ws, p->sk_counters, so[2]);
+        if (sh->sk[2]) { rc |= skinny_prepare(&sh->s_fc1[i], p->hn, D, static_cast<const bf16*>(hw.fc1_w), D, p1, EPI_BIAS_GELU_TANH, ws4[2], p->sk_counters, so[2]); sh->s_fc1[i].tag = tag; }
         else rc |= gemm_prepare(&sh->g_fc1[i], p->hn, D, static_cast<const bf16*>(hw.fc1_w), D, p1, EPI_BIAS_GELU_TANH);
-        if (sh->sk[3]) rc |= skinny_prepare(&sh->s_fc2[i], p->mlp, 4 * D, static_cast<const bf16*>(hw.fc2_w), 4 * D, p2, EPI_BIAS_GATE_RES, p->sk_ws, p->sk_counters, so[3], sh->fuse_ln ? &f_fc2 : nullptr);
+        if (sh->sk[3]) { rc |= skinny_prepare(&sh->s_fc2[i], p->mlp, 4 * D, static_cast<const bf16*>(hw.fc2_w), 4 * D, p2, EPI_BIAS_GATE_RES, ws4[3], p->sk_counters, so[3], sh->fuse_ln ? &f_fc2 : nullptr); sh->s_fc2[i].tag = tag; }
         else rc |= gemm_prepare(&sh->g_fc2[i], p->mlp, 4 * D, static_cast<const bf16*>(hw.fc2_w), 4 * D, p2, EPI_BIAS_GATE_RES);
     }
     rc |= gemm_prepare(&sh->g_final, p->hn, D, static_cast<const bf16*>(w.final_w), D, gp(p->yfin, 64, w.final_b, M, h->out_feat, D), EPI_BIAS);
@@ -345,6 +359,7 @@ int gtav_dit_plan_create(gtav_dit_t h, int B, int T, int cond_rows, void* worksp
     // on the caller's stream: the workspace may be a recycled block of a stream-ordered allocator (torch's), and the
     // plan's kernels run on that stream too - a memset on the legacy stream would order with neither
     if (rc == 0 && cudaMemsetAsync(p->sk_counters, 0, 2048, stream) != cudaSuccess) { set_error("dit_plan_create: clearing the split-K counters failed"); rc = -2; }
+    if (rc == 0 && p->sk_ws_bytes > 0 && cudaMemsetAsync(p->sk_ws, 0, 4 * p->sk_ws_bytes, stream) != cudaSuccess) { set_error("dit_plan_create: clearing the split-K workspace failed"); rc = -2; }
     if (rc) { delete p; return rc < 0 ? rc : -1; }
     *out = p;
     return 0;
@@ -383,7 +398,14 @@ int gtav_dit_context(gtav_dit_plan_t p, const void* x, int x_is_bf16, const int*
 int gtav_dit_last_frame(gtav_dit_plan_t p, const void* x, int x_is_bf16, const int* frame_row, void* out,
                         gtav_stream_t stream) {
     if (!p || !x || !out) { set_error("dit_last_frame: null argument"); return -1; }
-    return run_backbone(p, &p->last, MODE_LAST, x, x_is_bf16, p->T - 1, frame_row, out, stream);
+    if (p->sk_out_of_step) {
+        set_error("dit_last_frame: an earlier last-frame pass on this plan failed part-way, which leaves the split-K exchange's "
+                  "parities out of step; create a new plan");
+        return -3;
+    }
+    const int rc = run_backbone(p, &p->last, MODE_LAST, x, x_is_bf16, p->T - 1, frame_row, out, stream);
+    if (rc != 0 && tag_enabled()) p->sk_out_of_step = true;      // (get_error() still holds the failing launch's message)
+    return rc;
 }
 
 int gtav_dit_forward(gtav_dit_plan_t p, const void* x, int x_is_bf16, const int64_t* t, const float* actions,
@@ -415,11 +437,10 @@ int gtav_gemm_bf16(const void* A, int lda, const void* W, int ldw, void* out, in
 
 size_t gtav_gemm_skinny_workspace_bytes(int M) { return skinny_workspace_bytes(M); }
 
-int gtav_gemm_skinny_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
-                          int epilogue, const void* bias, const void* res, int ldr, const void* gate, int gate_ld,
-                          const int* frame_row, int rows_per_frame, int splits, void* workspace, int* counters,
-                          gtav_stream_t stream) {
-    if (!workspace || !counters) { set_error("gemm_skinny: workspace and counters are required"); return -1; }
+namespace {
+int skinny_standalone(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K, int epilogue,
+                      const void* bias, const void* res, int ldr, const void* gate, int gate_ld, const int* frame_row,
+                      int rows_per_frame, int splits, void* workspace, int* counters, int tag, gtav_stream_t stream) {
     GemmParams p{};
     p.out = static_cast<bf16*>(out); p.ldo = ldo; p.bias = static_cast<const bf16*>(bias);
     p.res = static_cast<const bf16*>(res); p.ldr = ldr; p.gate = static_cast<const bf16*>(gate); p.gate_ld = gate_ld;
@@ -429,8 +450,29 @@ int gtav_gemm_skinny_bf16(const void* A, int lda, const void* W, int ldw, void* 
     int rc = skinny_prepare(&op, static_cast<const bf16*>(A), lda, static_cast<const bf16*>(W), ldw, p, epilogue,
                             static_cast<float*>(workspace), counters, splits);
     if (rc) return rc;
+    op.tag = tag;
     if (const char* t = getenv("GTAV_SKINNY_TRACE")) op.trace = reinterpret_cast<long long*>(strtoull(t, nullptr, 0));
     return skinny_run(&op, stream);
+}
+}  // namespace
+
+int gtav_gemm_skinny_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
+                          int epilogue, const void* bias, const void* res, int ldr, const void* gate, int gate_ld,
+                          const int* frame_row, int rows_per_frame, int splits, void* workspace, int* counters,
+                          gtav_stream_t stream) {
+    if (!workspace || !counters) { set_error("gemm_skinny: workspace and counters are required"); return -1; }
+    return skinny_standalone(A, lda, W, ldw, out, ldo, M, N, K, epilogue, bias, res, ldr, gate, gate_ld, frame_row, rows_per_frame,
+                             splits, workspace, counters, 0, stream);
+}
+
+int gtav_gemm_skinny_tagged_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
+                                 int epilogue, const void* bias, const void* res, int ldr, const void* gate, int gate_ld,
+                                 const int* frame_row, int rows_per_frame, int splits, void* workspace, int parity,
+                                 gtav_stream_t stream) {
+    if (!workspace) { set_error("gemm_skinny_tagged: workspace is required"); return -1; }
+    if (parity != 0 && parity != 1) { set_error("gemm_skinny_tagged: parity must be 0 or 1, got %d", parity); return -1; }
+    return skinny_standalone(A, lda, W, ldw, out, ldo, M, N, K, epilogue, bias, res, ldr, gate, gate_ld, frame_row, rows_per_frame,
+                             splits, workspace, nullptr, 2 | parity, stream);
 }
 
 int gtav_ln_modulate(const void* x, void* out, int M, int D, const void* mod, int mod_ld, int shift_off, int scale_off,

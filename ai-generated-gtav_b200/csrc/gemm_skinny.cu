@@ -47,8 +47,58 @@ struct SkinnyParams {
     int gemm_ctas;         // (N/128) * splits; CTAs beyond that (fused modes) only take part in the per-token reduce
     float* ws;
     int* counters;
+    int tag;               // 0: rendezvous protocol; 2 | parity: tagged partial sums (see SkTag)
     long long* trace;      // optional [gridDim.x][8] globaltimer stamps (ns) of the phase boundaries; null in production
 };
+
+// Tagged partial sums: the exchange without fence, counter and poll.  The producer clears the lowest mantissa bit of every
+// fp32 partial sum and writes the launch's parity there; the consumer loads straight away and accepts an element once it
+// carries that parity, re-loading the ones that do not yet - every 4-byte element is its own ready flag, so no ordering
+// between elements is needed (relaxed gpu-scope stores and loads, L2 is the meeting point).  Stale elements always carry the
+// other parity because the caller (dit_engine.cu) gives each GEMM kind its own workspace, zeroed once, and alternates the
+// parity along the launches that share it: 1, 0, 1, 0 ... with an even number per pass.  Against the rendezvous protocol this
+// removes the gpu-scope fence after the stores, the atomic arrival, the polling round trip and two CTA barriers from the
+// critical path of every launch.  The sums lose their last mantissa bit (2^-24 relative, far below the bf16 rounding of the
+// Linear's output) and stay deterministic: summed in split order as before.  chk = 0: untagged, every element is accepted.
+#ifndef GTAV_SK_TAG_DELAY
+#define GTAV_SK_TAG_DELAY 600                      // SM clocks between a warp's last partial store and its first reduce load
+#endif
+#ifdef GTAV_SK_WEAK                                // A/B: the former .cg accesses instead of relaxed gpu-scope ones
+#define SK_LD "ld.global.cg"
+#define SK_ST "st.global.cg"
+#else
+#define SK_LD "ld.relaxed.gpu.global"
+#define SK_ST "st.relaxed.gpu.global"
+#endif
+struct SkTag {
+    uint32_t chk, par;
+};
+__device__ __forceinline__ bool tag_ok(uint32_t x, SkTag t) { return ((x ^ t.par) & t.chk) == 0u; }
+__device__ __forceinline__ bool tag_ok(uint2 v, SkTag t) { return (((v.x ^ t.par) | (v.y ^ t.par)) & t.chk) == 0u; }
+__device__ __forceinline__ bool tag_ok(uint4 v, SkTag t) {
+    return (((v.x ^ t.par) | (v.y ^ t.par) | (v.z ^ t.par) | (v.w ^ t.par)) & t.chk) == 0u;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u1(const float* p) {
+    uint32_t v;
+    asm volatile(SK_LD ".u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 ld_relaxed_u2(const float* p) {
+    uint2 v;
+    asm volatile(SK_LD ".v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ld_relaxed_u4(const float* p) {
+    uint4 v;
+    asm volatile(SK_LD ".v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u1(float* p, uint32_t v) {
+    asm volatile(SK_ST ".u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tag_spin_check(uint32_t& spins) {
+    if (++spins > (1u << 21)) __trap();          // a protocol bug (parity out of step) fails the launch instead of hanging
+}
 
 __device__ __forceinline__ long long globaltimer_ns() {
     long long t;
@@ -170,53 +220,91 @@ __device__ __noinline__ void skinny_store4(const GemmParams& g, int tok, int n, 
 // columns, loaded by the caller before the rendezvous.
 template <int EPI, int S>
 __device__ __forceinline__ void skinny_reduce(const GemmParams& g, const float* part, int total, int lo, int hi, int wid, int lane,
-                                              int n0, uint2 bias) {
+                                              int n0, uint2 bias, SkTag tg) {
+    static_assert(S <= 4, "the unrolled reduce is instantiated for S = 4 only; other split counts use skinny_reduce_any");
     const float* base = part + 4 * lane;
-    if (S <= 4) {
-        // few splits: a warp's tokens (at most 5 per 144-token tile share) are loaded together, so the whole reduce costs
-        // one L2 round trip instead of one per token
-        constexpr int IT = 5;
+    const uint32_t keep = ~tg.chk;
+    // few splits: a warp's tokens (at most 5 per 144-token tile share) are loaded together, so the whole reduce costs
+    // one L2 round trip instead of one per token (tagged: plus one per round of elements that had not arrived yet)
+    constexpr int IT = 5;
 #pragma unroll 1
-        for (int t0 = lo + wid; t0 < hi; t0 += 8 * IT) {
-            float4 v[IT][S];
+    for (int t0 = lo + wid; t0 < hi; t0 += 8 * IT) {
+        // first attempt: every load of the warp's tokens back to back; then only what had not arrived yet is loaded again
+        uint4 v[IT][S];
+        uint32_t pending = 0u, spins = 0u;
 #pragma unroll
-            for (int it = 0; it < IT; ++it) {
-                const int tok = t0 + 8 * it;
+        for (int it = 0; it < IT; ++it)
+#pragma unroll
+            for (int s2 = 0; s2 < S; ++s2)
+                if (t0 + 8 * it < hi) v[it][s2] = ld_relaxed_u4(base + (static_cast<size_t>(s2) * total + t0 + 8 * it) * 128);
+#pragma unroll
+        for (int it = 0; it < IT; ++it)
+#pragma unroll
+            for (int s2 = 0; s2 < S; ++s2)
+                if (t0 + 8 * it < hi && !tag_ok(v[it][s2], tg)) pending |= 1u << (S * it + s2);
+        while (pending) {                          // (all missing loads in flight together, then the checks)
+            tag_spin_check(spins);
+#pragma unroll
+            for (int it = 0; it < IT; ++it)
 #pragma unroll
                 for (int s2 = 0; s2 < S; ++s2)
-                    if (tok < hi) v[it][s2] = __ldcg(reinterpret_cast<const float4*>(base + (static_cast<size_t>(s2) * total + tok) * 128));
-            }
+                    if (pending >> (S * it + s2) & 1u) v[it][s2] = ld_relaxed_u4(base + (static_cast<size_t>(s2) * total + t0 + 8 * it) * 128);
 #pragma unroll
-            for (int it = 0; it < IT; ++it) {
-                const int tok = t0 + 8 * it;
-                if (tok < hi) {
-                    float4 acc = v[it][0];
+            for (int it = 0; it < IT; ++it)
 #pragma unroll
-                    for (int s2 = 1; s2 < S; ++s2) { acc.x += v[it][s2].x; acc.y += v[it][s2].y; acc.z += v[it][s2].z; acc.w += v[it][s2].w; }
-                    skinny_store4<EPI>(g, tok, n0 + 4 * lane, acc, bias);
+                for (int s2 = 0; s2 < S; ++s2)
+                    if ((pending >> (S * it + s2) & 1u) && tag_ok(v[it][s2], tg)) pending &= ~(1u << (S * it + s2));
+        }
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            const int tok = t0 + 8 * it;
+            if (tok < hi) {
+                float4 acc = make_float4(__uint_as_float(v[it][0].x & keep), __uint_as_float(v[it][0].y & keep),
+                                         __uint_as_float(v[it][0].z & keep), __uint_as_float(v[it][0].w & keep));
+#pragma unroll
+                for (int s2 = 1; s2 < S; ++s2) {
+                    acc.x += __uint_as_float(v[it][s2].x & keep); acc.y += __uint_as_float(v[it][s2].y & keep);
+                    acc.z += __uint_as_float(v[it][s2].z & keep); acc.w += __uint_as_float(v[it][s2].w & keep);
                 }
+                skinny_store4<EPI>(g, tok, n0 + 4 * lane, acc, bias);
             }
         }
-    } else {
-        static_assert(S <= 4, "the unrolled reduce is instantiated for S = 4 only; other split counts use skinny_reduce_any");
     }
 }
 
 // Sum of the S partials at p0, p0 + stride, ... in split order, all loads in flight together.
 template <int S>
-__device__ __forceinline__ float4 skinny_sum4(const float* p0, size_t stride) {
-    float4 v[S];
+__device__ __forceinline__ float4 skinny_sum4(const float* p0, size_t stride, SkTag tg) {
+    uint4 v[S];
+    const uint32_t keep = ~tg.chk;
+    uint32_t pending = 0u, spins = 0u;
 #pragma unroll
-    for (int s2 = 0; s2 < S; ++s2) v[s2] = __ldcg(reinterpret_cast<const float4*>(p0 + s2 * stride));
-    float4 acc = v[0];
+    for (int s2 = 0; s2 < S; ++s2) v[s2] = ld_relaxed_u4(p0 + s2 * stride);
 #pragma unroll
-    for (int s2 = 1; s2 < S; ++s2) { acc.x += v[s2].x; acc.y += v[s2].y; acc.z += v[s2].z; acc.w += v[s2].w; }
+    for (int s2 = 0; s2 < S; ++s2)
+        if (!tag_ok(v[s2], tg)) pending |= 1u << s2;
+    while (pending) {                              // only what had not arrived yet is loaded again
+        tag_spin_check(spins);
+#pragma unroll
+        for (int s2 = 0; s2 < S; ++s2)
+            if (pending >> s2 & 1u) v[s2] = ld_relaxed_u4(p0 + s2 * stride);
+#pragma unroll
+        for (int s2 = 0; s2 < S; ++s2)
+            if ((pending >> s2 & 1u) && tag_ok(v[s2], tg)) pending &= ~(1u << s2);
+    }
+    float4 acc = make_float4(__uint_as_float(v[0].x & keep), __uint_as_float(v[0].y & keep), __uint_as_float(v[0].z & keep),
+                             __uint_as_float(v[0].w & keep));
+#pragma unroll
+    for (int s2 = 1; s2 < S; ++s2) {
+        acc.x += __uint_as_float(v[s2].x & keep); acc.y += __uint_as_float(v[s2].y & keep);
+        acc.z += __uint_as_float(v[s2].z & keep); acc.w += __uint_as_float(v[s2].w & keep);
+    }
     return acc;
 }
 // Any split count: one token per warp at a time, partials summed in split order, up to 16 loads in flight.
 template <int EPI>
 __device__ __forceinline__ void skinny_reduce_any(const GemmParams& g, const float* part, int S, int total, int lo, int hi, int wid,
-                                                  int lane, int n0, uint2 bias) {
+                                                  int lane, int n0, uint2 bias, SkTag tg) {
     const float* base = part + 4 * lane;
     const size_t stride = static_cast<size_t>(total) * 128;
 #pragma unroll 1
@@ -224,9 +312,9 @@ __device__ __forceinline__ void skinny_reduce_any(const GemmParams& g, const flo
         const float* p0 = base + static_cast<size_t>(tok) * 128;
         float4 acc;
         switch (S) {
-            case 2: acc = skinny_sum4<2>(p0, stride); break;
-            case 8: acc = skinny_sum4<8>(p0, stride); break;
-            default: acc = skinny_sum4<16>(p0, stride); break;
+            case 2: acc = skinny_sum4<2>(p0, stride, tg); break;
+            case 8: acc = skinny_sum4<8>(p0, stride, tg); break;
+            default: acc = skinny_sum4<16>(p0, stride, tg); break;
         }
         skinny_store4<EPI>(g, tok, n0 + 4 * lane, acc, bias);
     }
@@ -260,7 +348,7 @@ __device__ __forceinline__ Epi4Ops skinny_ln_preload(const SkinnyParams& p, int 
     return e;
 }
 __device__ __forceinline__ void skinny_reduce_ln(const SkinnyParams& p, int S, int total, int warp, int lane, uint8_t* smod,
-                                                 uint8_t* srow, Epi4Ops e) {
+                                                 uint8_t* srow, Epi4Ops e, SkTag tg) {
     const GemmParams& g = p.g;
     const SkinnyFuseParams& f = p.f;
     const int n = warp * 128 + 4 * lane;
@@ -272,9 +360,9 @@ __device__ __forceinline__ void skinny_reduce_ln(const SkinnyParams& p, int S, i
         const float* p0 = base + static_cast<size_t>(tok) * 128;
         float4 acc;
         switch (S) {                           // only the partial-sum loads depend on S: one copy of everything else
-            case 4: acc = skinny_sum4<4>(p0, stride); break;
-            case 8: acc = skinny_sum4<8>(p0, stride); break;
-            default: acc = skinny_sum4<16>(p0, stride); break;
+            case 4: acc = skinny_sum4<4>(p0, stride, tg); break;
+            case 8: acc = skinny_sum4<8>(p0, stride, tg); break;
+            default: acc = skinny_sum4<16>(p0, stride, tg); break;
         }
         const uint2 o = skinny_epi4<EPI_BIAS_GATE_RES>(acc, e);
         *reinterpret_cast<uint2*>(g.out + static_cast<size_t>(tok) * g.ldo + n) = o;
@@ -320,29 +408,59 @@ __device__ __forceinline__ void skinny_tattn_preload(const SkinnyParams& p, int 
     }
 }
 template <int S>
-__device__ __forceinline__ void skinny_reduce_tattn(const SkinnyParams& p, int total, int warp, int lane, TattnPre& pre) {
+__device__ __forceinline__ void skinny_reduce_tattn(const SkinnyParams& p, int total, int warp, int lane, TattnPre& pre, SkTag tg) {
     const GemmParams& g = p.g;
+    const uint32_t keep = ~tg.chk;
     const int tc = p.f.ctx_frames;
     const float2 cs = p.f.rot[tc * 32 + lane];
 #pragma unroll 1
     for (int tok = blockIdx.x; tok < total; tok += gridDim.x) {
-        float2 a[2][3][S];
+        uint2 a[2][3][S];
+        uint32_t pending = 0u, spins = 0u;                                   // 6 S <= 24 loads
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
             for (int part = 0; part < 3; ++part) {
                 const float* base = p.ws + (static_cast<size_t>(part * 8 + warp) * S * total + tok) * 128 + hh * 64 + 2 * lane;
 #pragma unroll
-                for (int s2 = 0; s2 < S; ++s2) a[hh][part][s2] = __ldcg(reinterpret_cast<const float2*>(base + static_cast<size_t>(s2) * total * 128));
+                for (int s2 = 0; s2 < S; ++s2) a[hh][part][s2] = ld_relaxed_u2(base + static_cast<size_t>(s2) * total * 128);
             }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+            for (int part = 0; part < 3; ++part)
+#pragma unroll
+                for (int s2 = 0; s2 < S; ++s2)
+                    if (!tag_ok(a[hh][part][s2], tg)) pending |= 1u << ((hh * 3 + part) * S + s2);
+        while (pending) {                          // only what had not arrived yet is loaded again
+            tag_spin_check(spins);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int part = 0; part < 3; ++part) {
+                    const float* base = p.ws + (static_cast<size_t>(part * 8 + warp) * S * total + tok) * 128 + hh * 64 + 2 * lane;
+#pragma unroll
+                    for (int s2 = 0; s2 < S; ++s2)
+                        if (pending >> ((hh * 3 + part) * S + s2) & 1u) a[hh][part][s2] = ld_relaxed_u2(base + static_cast<size_t>(s2) * total * 128);
+                }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int part = 0; part < 3; ++part)
+#pragma unroll
+                    for (int s2 = 0; s2 < S; ++s2) {
+                        const int bit = (hh * 3 + part) * S + s2;
+                        if ((pending >> bit & 1u) && tag_ok(a[hh][part][s2], tg)) pending &= ~(1u << bit);
+                    }
+        }
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
             float2 qkv[3];
 #pragma unroll
             for (int part = 0; part < 3; ++part) {
-                float2 acc = a[hh][part][0];
+                float2 acc = make_float2(__uint_as_float(a[hh][part][0].x & keep), __uint_as_float(a[hh][part][0].y & keep));
 #pragma unroll
-                for (int s2 = 1; s2 < S; ++s2) { acc.x += a[hh][part][s2].x; acc.y += a[hh][part][s2].y; }
+                for (int s2 = 1; s2 < S; ++s2) { acc.x += __uint_as_float(a[hh][part][s2].x & keep); acc.y += __uint_as_float(a[hh][part][s2].y & keep); }
                 qkv[part] = make_float2(bf16_round(acc.x), bf16_round(acc.y));       // the Linear's bf16 output
             }
             *reinterpret_cast<uint32_t*>(g.out + static_cast<size_t>(tok) * g.ldo + (2 * warp + hh) * 64 + 2 * lane) =
@@ -376,6 +494,10 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     const int kc0 = split * chunks;
     const int total = tiles * SK_NT;
     const uint32_t tmem_cols = total <= 256 ? 256u : 512u;
+    const bool tagged = p.tag != 0;                // tagged partial sums instead of the counter rendezvous (SkTag)
+    SkTag tg;
+    tg.chk = tagged ? 1u : 0u;
+    tg.par = tagged ? static_cast<uint32_t>(p.tag & 1) : 0u;
 
     // Both operand loads go out BEFORE the CTA-wide set-up barrier: thread 0 initialises the W barrier and requests the
     // W slab at once (weights do not depend on the previous kernel), warp 1 initialises the token-slab barriers, waits for
@@ -455,7 +577,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     int* const meet = p.counters + 4 * (FUSE == SK_FUSE_NONE ? rb : 64);
     const int meet_n = FUSE == SK_FUSE_NONE ? S : static_cast<int>(gridDim.x);
     int sense0 = 0;
-    if (threadIdx.x == 128 && meet_n > 1) sense0 = ld_acquire_gpu(meet + 2);
+    if (threadIdx.x == 128 && meet_n > 1 && !tagged) sense0 = ld_acquire_gpu(meet + 2);
     Epi4Ops epre;
     epre.bias = epre.gate = epre.res = make_uint2(0u, 0u);
     TattnPre tpre;
@@ -502,6 +624,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         const int c0 = warp < 4 ? half : 0;
         const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0;
         float* mine = p.ws + static_cast<size_t>(blockIdx.x) * total * 128 + static_cast<size_t>(c0) * 128 + row;
+        const uint32_t keep = ~tg.chk;
 #pragma unroll 1
         for (int c = 0; c < half; c += 24) {                                   // half = 72 * tiles
             uint32_t v[3][8];
@@ -511,56 +634,80 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 3; ++j)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) __stcg(mine + static_cast<size_t>(c + 8 * j + i) * 128, __uint_as_float(v[j][i]));
+                for (int i = 0; i < 8; ++i) st_relaxed_u1(mine + static_cast<size_t>(c + 8 * j + i) * 128, (v[j][i] & keep) | tg.par);
         }
-        // release: partial stores ordered before the arrival below - CTA barrier, then ONE gpu-scope fence by the arriving
-        // thread (cumulative over the barrier, the grid-sync idiom), then the relaxed atomic.  GTAV_SK_FENCE_ALL: every
-        // thread fences before the barrier instead (the former arrangement), kept for A/B measurement.
+        if (!tagged) {
+            // release: partial stores ordered before the arrival below - CTA barrier, then ONE gpu-scope fence by the arriving
+            // thread (cumulative over the barrier, the grid-sync idiom), then the relaxed atomic.  GTAV_SK_FENCE_ALL: every
+            // thread fences before the barrier instead (the former arrangement), kept for A/B measurement.
 #ifdef GTAV_SK_FENCE_ALL
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-#endif
-        tcgen05_fence_before();
-        __syncthreads();
-        if (warp == 2) {                           // the accumulator has been read by everyone: give the TMEM back now,
-            tcgen05_fence_after();                 // off the kernel's exit path
-            tmem_dealloc(tmem_base, tmem_cols);
-        }
-        if (threadIdx.x == 128) {
-#ifndef GTAV_SK_FENCE_ALL
             asm volatile("fence.acq_rel.gpu;" ::: "memory");
 #endif
-            SK_STAMP(5);                                                       // partials written + fenced
-            skinny_rendezvous(meet, meet_n, sense0);
+            tcgen05_fence_before();
+            __syncthreads();
+            if (warp == 2) {                           // the accumulator has been read by everyone: give the TMEM back now,
+                tcgen05_fence_after();                 // off the kernel's exit path
+                tmem_dealloc(tmem_base, tmem_cols);
+            }
+            if (threadIdx.x == 128) {
+#ifndef GTAV_SK_FENCE_ALL
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
+                SK_STAMP(5);                                                       // partials written + fenced
+                skinny_rendezvous(meet, meet_n, sense0);
+            }
+        } else {
+            if (threadIdx.x == 128) SK_STAMP(5);                                   // this warp's partials issued
+            // The other CTAs' partial sums become visible ~0.5 us after they were issued; loads sent before that come back
+            // without them and cost a second round trip.  Wait that long before the first attempt.
+            if (GTAV_SK_TAG_DELAY > 0) {
+                const long long t0 = clock64();
+                while (clock64() - t0 < GTAV_SK_TAG_DELAY) {}
+            }
+            if (threadIdx.x == 128) SK_STAMP(6);
         }
-    } else if (FUSE != SK_FUSE_NONE && threadIdx.x == 128) {
+    } else if (FUSE != SK_FUSE_NONE && !tagged && threadIdx.x == 128) {
         skinny_rendezvous(meet, meet_n, sense0);                               // reduce-only CTA: nothing to publish
+    } else if (FUSE != SK_FUSE_NONE && tagged) {
+        // reduce-only CTA: its partial sums will not exist for a few microseconds - one thread watches a single element of the
+        // CTA's first token row (last row block, last split) instead of all 256 re-loading whole rows through L2 meanwhile
+        if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < total) {
+            const float* probe = p.ws + (static_cast<size_t>(p.gemm_ctas - 1) * total + blockIdx.x) * 128 + 127;
+            uint32_t spins = 0u;
+            while (!tag_ok(ld_relaxed_u1(probe), tg)) tag_spin_check(spins);
+        }
+        __syncthreads();
     }
     if (S > 1 && FUSE == SK_FUSE_NONE) {
-        // all 8 warps reduce once the rendezvous of the row block has completed
-        __syncthreads();
-        if (threadIdx.x == 128) SK_STAMP(6);                                   // rendezvous passed
+        // all 8 warps reduce once the rendezvous of the row block has completed (tagged: each warp as soon as it has stored)
+        if (!tagged) {
+            __syncthreads();
+            if (threadIdx.x == 128) SK_STAMP(6);                               // rendezvous passed
+        }
         const GemmParams& g = p.g;
         const int lo = split * total / S, hi = (split + 1) * total / S;
         const float* part = p.ws + static_cast<size_t>(rb) * S * total * 128;
         // S = 4 (to_qkv, to_out, fc1 of one rollout: the hot launches) gets the fully unrolled reduce with every load of
         // a warp's tokens in flight at once; the other split counts share one run-time loop - four unrolled variants
         // made these latency-bound kernels ~50 % larger, and instruction fetch is a measured cost for them.
-        if (S == 4) skinny_reduce<EPI, 4>(g, part, total, lo, hi, warp, lane, rb * 128, epre.bias);
-        else skinny_reduce_any<EPI>(g, part, S, total, lo, hi, warp, lane, rb * 128, epre.bias);
+        if (S == 4) skinny_reduce<EPI, 4>(g, part, total, lo, hi, warp, lane, rb * 128, epre.bias, tg);
+        else skinny_reduce_any<EPI>(g, part, S, total, lo, hi, warp, lane, rb * 128, epre.bias, tg);
         if (threadIdx.x == 128) SK_STAMP(7);                                   // reduced + stored (this warp)
     }
     if (FUSE != SK_FUSE_NONE) {
-        // ---- every CTA has met every other one (thread 128 above): it now owns whole token rows
-        __syncthreads();
-        if (threadIdx.x == 128) SK_STAMP(6);
+        // ---- every CTA has met every other one (thread 128 above; tagged: the loads themselves wait): it now owns whole token rows
+        if (!tagged) {
+            __syncthreads();
+            if (threadIdx.x == 128) SK_STAMP(6);
+        }
         if (FUSE == SK_FUSE_LN) {
-            skinny_reduce_ln(p, S, total, warp, lane, smod, srow, epre);       // S in {4, 8, 16} (checked on the host)
+            skinny_reduce_ln(p, S, total, warp, lane, smod, srow, epre, tg);   // S in {4, 8, 16} (checked on the host)
         } else {
-            skinny_reduce_tattn<4>(p, total, warp, lane, tpre);                // S == 4, <= 7 cached frames (checked on the host)
+            skinny_reduce_tattn<4>(p, total, warp, lane, tpre, tg);            // S == 4, <= 7 cached frames (checked on the host)
         }
         if (threadIdx.x == 128) SK_STAMP(7);
     }
-    if (S == 1 && gemm_cta) {                      // no split: the epilogue warps read the accumulator until here
+    if ((S == 1 || tagged) && gemm_cta) {          // no split / tagged: warps read the accumulator until shortly before here
         tcgen05_fence_before();
         __syncthreads();
         if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
@@ -628,6 +775,7 @@ int skinny_prepare(SkinnyOp* op, const bf16* A, int lda, const bf16* W, int ldw,
     op->ws = ws;
     op->counters = counters;
     op->trace = nullptr;
+    op->tag = 0;
     op->f = SkinnyFuseParams{};
     op->grid = rbs * S;
     if (fuse != nullptr && fuse->mode != SK_FUSE_NONE) {
@@ -664,6 +812,7 @@ static int skinny_launch(const SkinnyOp* op, cudaStream_t stream) {
     sp.g = op->p; sp.f = op->f; sp.splits = op->splits; sp.chunks = op->chunks; sp.tiles = op->tiles; sp.ws = op->ws;
     sp.counters = op->counters; sp.gemm_ctas = (op->p.N / 128) * op->splits;
     sp.trace = op->trace;
+    sp.tag = op->tag;
     // At least half of the SM's shared memory, so that exactly one CTA of this kernel fits on an SM: the CTAs of a
     // row block wait for each other, and a second CTA on the same SM could block in tcgen05.alloc behind a waiting one.
     // (Two CTAs per SM - the next launch starting under the current one - was measured and dropped: TMA loads of an

@@ -124,6 +124,9 @@ struct SkinnyOp {
     int epi, splits, chunks, tiles;
     float* ws;        // fp32 partial-sum workspace, skinny_workspace_bytes(M)
     int* counters;    // 512 ints, zero before the first launch (rendezvous groups of 4 ints, maintained by the kernel)
+    int tag;          // 0 (skinny_prepare's default): CTAs meet on `counters`.  2 | parity: tagged partial sums, no rendezvous -
+                      // the caller owns the protocol: `ws` is used by launches of THIS shape and split only, was zeroed once,
+                      // and consecutive launches on it alternate the parity starting with 1 (gemm_skinny.cu, SkTag)
     long long* trace; // optional phase time stamps [CTAs][8] (profiling aid), normally null
 };
 bool skinny_supported(int M, int N, int K, int epi);

@@ -246,17 +246,19 @@ def skinny_roofline(dit, B, pk):
     o3 = torch.empty((M, 3 * D), device=dev, dtype=torch.bfloat16)
     o4 = torch.empty((M, 4 * D), device=dev, dtype=torch.bfloat16)
     bias = torch.zeros(4 * D, device=dev, dtype=torch.bfloat16)
-    ws = torch.empty(lib.gtav_gemm_skinny_workspace_bytes(M), dtype=torch.uint8, device=dev)
-    counters = torch.zeros(512, dtype=torch.int32, device=dev)
+    # the exchange the engine's last-frame pass uses: partial sums tagged with the launch's parity, one zeroed workspace per
+    # GEMM shape, parity alternating along the (even number of) launches that share it (include/gtav_b200.h)
     halves = _hot_weights(dit)
+    assert len(halves) % 2 == 0
     shapes = [(0, a1, o3, 3 * D, D, N.EPI_STORE), (1, a1, o1, D, D, N.EPI_BIAS), (3, a1, o4, 4 * D, D, N.EPI_BIAS_GELU_TANH),
               (5, a4, o1, D, 4 * D, N.EPI_BIAS)]
+    wss = [torch.zeros(lib.gtav_gemm_skinny_workspace_bytes(M), dtype=torch.uint8, device=dev) for _ in shapes]
     def one_pass():
-        for h in halves:
-            for wi, a, out, n, k, epi in shapes:
-                N.check(lib.gtav_gemm_skinny_bf16(a.data_ptr(), k, h[wi].data_ptr(), k, out.data_ptr(), n, M, n, k, epi, bias.data_ptr(),
-                                                  None, 0, None, 0, None, 144, 0, ws.data_ptr(), counters.data_ptr(), N.current_stream()),
-                        "gemm_skinny")
+        for i, h in enumerate(halves):
+            for (wi, a, out, n, k, epi), ws in zip(shapes, wss):
+                N.check(lib.gtav_gemm_skinny_tagged_bf16(a.data_ptr(), k, h[wi].data_ptr(), k, out.data_ptr(), n, M, n, k, epi, bias.data_ptr(),
+                                                         None, 0, None, 0, None, 144, 0, ws.data_ptr(), (i & 1) ^ 1, N.current_stream()),
+                        "gemm_skinny_tagged")
     ms = _time_passes(one_pass)
     per_half = sum(2 * (n * k + M * k + M * n) for _, _, _, n, k, _ in shapes)          # bf16 bytes: W + A + out
     gb = len(halves) * per_half / 1e9
@@ -266,10 +268,12 @@ def skinny_roofline(dit, B, pk):
                 kernel="gemm_skinny_kernel (tcgen05 weight-streaming GEMM, 128 launches per last-frame DiT step)",
                 algorithmic_mb_per_launch=round(gb * 1e3 / (4 * len(halves)), 3), us_per_launch=round(ms * 1e3 / (4 * len(halves)), 3),
                 gemm_ms_per_last_frame_step=round(ms, 4), peak_source=f"{pk['src']} HBM copy bandwidth",
-                note="latency-bound, not bandwidth-bound: a launch is a chain of L2 round trips (CTA entry + set-up 0.35 us, operand "
-                     "slabs 0.8-1.4, MMA 0.8, split-K partials out 1.9, rendezvous 0.7-0.9, reduce + fused LayerNorm / temporal "
-                     "attention 1.5-2.0, next kernel's CTAs 0.6-0.9 later; profiles/r02/skinny_in_step_trace_b.txt); its DRAM "
-                     "traffic equals the algorithmic bytes (profiles/r02/roofline_traffic.json)")
+                note="bound by L2 traffic and latency, not by HBM: per launch the L2 fabric moves the weights (8 MB), the token slabs of "
+                     "every row block (10.6 MB) and the split-K partial sums out and back (2 x 10.9 MB) - ~41 MB in ~6.5 us - in a "
+                     "chain of phases (CTA entry + set-up 0.2 us, operand slabs 1.5, MMA 0.8, tagged partials out 1.2, reduce + fused "
+                     "LayerNorm / temporal attention 2.0-3.5, next kernel's CTAs 0.6-1.0 later; "
+                     "profiles/r02/skinny_in_step_trace_tagged.txt); its DRAM traffic equals the algorithmic bytes "
+                     "(profiles/r02/roofline_traffic.json)")
 
 
 def cpu_c1_run(init="initB", dit_steps_budget=None):

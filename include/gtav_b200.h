@@ -67,6 +67,17 @@ int gtav_gemm_skinny_bf16(const void* A, int lda, const void* W, int ldw, void* 
                           int epilogue, const void* bias, const void* res, int ldr, const void* gate, int gate_ld,
                           const int* frame_row, int rows_per_frame, int splits, void* workspace, int* counters,
                           gtav_stream_t stream);
+/* The same GEMM with the split-K exchange the DiT engine uses for its last-frame passes (csrc/gemm_skinny.cu, SkTag): the
+ * partial sums carry the launch's parity in their last mantissa bit and the reducing CTAs accept an element once it shows
+ * it - no fence, counter or poll between the two halves of the kernel.  The caller owns the protocol: `workspace` is used
+ * by launches of ONE (M, N, K, splits) shape only, was zeroed before the first of them, and parity alternates 1, 0, 1, 0 ...
+ * from launch to launch on it (a captured graph must hold an even number of them).  A parity out of step fails the launch
+ * (trap after a bounded spin) instead of hanging.  Results differ from gtav_gemm_skinny_bf16 by that cleared bit of
+ * each fp32 partial sum only. */
+int gtav_gemm_skinny_tagged_bf16(const void* A, int lda, const void* W, int ldw, void* out, int ldo, int M, int N, int K,
+                                 int epilogue, const void* bias, const void* res, int ldr, const void* gate, int gate_ld,
+                                 const int* frame_row, int rows_per_frame, int splits, void* workspace, int parity,
+                                 gtav_stream_t stream);
 
 /* modulate(LayerNorm(x), shift, scale) of dit.py:19-27 -> bf16 [M, D]; D = 1024. */
 int gtav_ln_modulate(const void* x, void* out, int M, int D, const void* mod, int mod_ld, int shift_off, int scale_off,

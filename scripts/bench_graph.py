@@ -129,7 +129,7 @@ def engine_steps():
                        ("to_out with 16 K-splits", {"GTAV_SK_SPLITS": "0,16,0,0"}),
                        ("tiled GEMM everywhere", {"GTAV_SKINNY": "0"}),
                        ("no PDL", {"GTAV_PDL_OFF_NOTE": "set GTAV_PDL=0 before start to test"})):
-        if "GTAV_PDL_OFF_NOTE" in env:
+        if "GTAV_PDL_OFF_NOTE" in env or (env and "--default-only" in sys.argv):
             continue
         for k, v in env.items():
             os.environ[k] = v

@@ -361,6 +361,32 @@ def test_skinny_gemm_epilogues_and_reuse(lib):
     assert int(st[8:].abs().sum()) == 0 and bool(((st[:8, 0] == 0) | (st[:8, 1] == 0)).all())
 
 
+def test_skinny_tagged_exchange(lib):
+    """gtav_gemm_skinny_tagged_bf16: partial sums tagged with the launch's parity instead of the counter rendezvous.  Four
+    launches on one zeroed workspace with parity 1, 0, 1, 0 (fresh inputs each time, so a stale partial sum accepted by
+    mistake would show) against the fp32 product and against the counter version, every split count and 1-3 frame tiles."""
+    N = _N()
+    for M, Nn, K, splits in ((144, 3072, 1024, 0), (144, 1024, 4096, 0), (288, 1024, 1024, 0), (432, 256, 512, 8), (144, 128, 256, 2)):
+        ws = torch.zeros(lib.gtav_gemm_skinny_workspace_bytes(M), dtype=torch.uint8, device="cuda")
+        g = torch.Generator(device="cuda").manual_seed(M + Nn + K)
+        bias = (torch.randn((Nn,), device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+        for launch in range(4):
+            A = torch.randn((M, K), device="cuda", generator=g).to(torch.bfloat16)
+            W = (torch.randn((Nn, K), device="cuda", generator=g) / math.sqrt(K)).to(torch.bfloat16)
+            out = torch.zeros((M, Nn), dtype=torch.bfloat16, device="cuda")
+            N.check(lib.gtav_gemm_skinny_tagged_bf16(A.data_ptr(), K, W.data_ptr(), K, out.data_ptr(), Nn, M, Nn, K, N.EPI_BIAS,
+                                                     bias.data_ptr(), None, 0, None, 0, None, 144, splits, ws.data_ptr(),
+                                                     (launch & 1) ^ 1, N.current_stream()), "gemm_skinny_tagged")
+            torch.cuda.synchronize()
+            close_bf16(out, A.float() @ W.float().t() + bias.float())
+            ref = run_skinny(lib, A, W, N.EPI_BIAS, bias=bias, splits=splits)
+            d = (out.float() - ref.float()).abs()
+            assert float((d > 0).float().mean()) < 1e-3 and float(d.max()) <= 2 ** -7 * float(ref.float().abs().max())
+    with pytest.raises(RuntimeError, match="parity"):
+        N.check(lib.gtav_gemm_skinny_tagged_bf16(A.data_ptr(), K, W.data_ptr(), K, out.data_ptr(), Nn, M, Nn, K, N.EPI_BIAS, bias.data_ptr(),
+                                                 None, 0, None, 0, None, 144, splits, ws.data_ptr(), 2, N.current_stream()), "gemm_skinny_tagged")
+
+
 def test_skinny_matches_tiled_gemm(lib):
     """Same inputs through both GEMM kernels: only the fp32 summation order differs."""
     N = _N()

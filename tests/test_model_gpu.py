@@ -134,6 +134,44 @@ def test_fused_reduce_equals_separate_kernels(monkeypatch):
         assert torch.isfinite(a.float()).all()
         assert torch.equal(a, b), f"case {i}: fused reduce differs from separate kernels, max-abs {float((a.float() - b.float()).abs().max())}"
 
+@pytest.mark.gpu
+def test_tagged_exchange_matches_counter_rendezvous(monkeypatch):
+    """The weight-streaming GEMMs exchange their split-K partial sums tagged with the launch's parity in the last mantissa
+    bit (default; gemm_skinny.cu, SkTag) instead of meeting on a counter (GTAV_SK_TAG=0).  Same sums in the same order up to
+    that cleared bit of each fp32 partial - flips of single bf16 roundings that the following layers spread like any change
+    of summation order (cf. test_dit_last_frame_split_equals_dense: 2e-2 at depth 2), so the bound is a few bf16 ulps.
+    Repeated passes on one plan give the same bits (every pass leaves each workspace at parity 0), for 1, 2 and 3 rollouts
+    and with or without the fused reduces."""
+    from gtav_b200.model.dit import DiT
+    sd = make_dit_state(DiTConfig(depth=3), seed=0)
+    cases = ((1, 5, 191, True), (2, 4, 192, True), (3, 3, 193, False), (1, 1, 194, False))
+    for fuse in ("1", "0"):
+        outs = {}
+        for tag in ("1", "0"):
+            monkeypatch.setenv("GTAV_FUSE", fuse)
+            monkeypatch.setenv("GTAV_SK_TAG", tag)
+            monkeypatch.setenv("GTAV_SKINNY", "1")
+            model = DiT(depth=3)
+            model.load_state_dict(sd, strict=True)
+            model = model.cuda().eval()
+            res = []
+            for B, T, seed, actions in cases:
+                x = seeded_randn((B, T, 16, 18, 32), seed).cuda()
+                t = torch.randint(0, 1000, (B, T), generator=torch.Generator().manual_seed(seed)).cuda()
+                a = w_key_actions(B, T).cuda() if actions else None
+                first = model.forward_last_frame(x, t, a).clone()
+                for _ in range(2):                                   # the same plan again: parity state must be back at its start
+                    assert torch.equal(model.forward_last_frame(x, t, a), first)
+                res.append(first)
+            outs[tag] = res
+        for i, (a, b) in enumerate(zip(outs["1"], outs["0"])):
+            assert torch.isfinite(a.float()).all()
+            d = (a.float() - b.float()).abs()
+            print(f"tagged vs counter exchange (fuse={fuse}, case {i}): max-abs {float(d.max()):.5f} mean-abs {float(d.mean()):.6f} "
+                  f"differing {float((d > 0).float().mean()):.4f}")
+            assert float(d.max()) <= 4e-2 and float(d.mean()) <= 3e-3
+
+
 
 def test_last_frame_pass_full_depth_vs_reference_golden(golden):
     """The frame-cache split (context pass + weight-streaming last-frame pass) on the real 16-block DiT (B = 1, T = 5): last
