@@ -15,13 +15,15 @@
 //     alternatives for the operand loads, all slower in the real step (profiles/r01/bench_engine_v6.log): 2 / 4 boxes
 //     per operand from different warps (+1 % / +8 % step time: every extra TMA instruction costs), the token slab
 //     through cp.async with a software swizzle next to the TMA-loaded weights (+6 %);
-//   * partial accumulators go to an fp32 workspace (L2; released by one gpu-scope fence of the arriving thread after the
-//     CTA barrier), the S CTAs of a row block meet on a
-//     counter, and each reduces + runs the fused epilogue for its 1/S share of the tokens, summing
-//     the partials in split order (deterministic);
+//   * partial accumulators go to an fp32 workspace (L2) and each of the S CTAs of a row block reduces + runs the fused
+//     epilogue for its 1/S share of the tokens, summing the partials in split order (deterministic).  How a CTA knows
+//     that the others' partial sums are there: in the engine's passes every element carries the launch's parity in its
+//     last mantissa bit and is its own ready flag (SkTag below: no fence, counter, poll or CTA barrier); stand-alone
+//     calls and GTAV_SK_TAG=0 release the stores with one gpu-scope fence of the arriving thread after a CTA barrier
+//     and meet on a counter;
 //   * optionally the reduce is done per token row by every CTA (plus reduce-only CTAs up to one per token), which lets
 //     the row-wise kernel that would follow - LayerNorm + modulate, or the last-frame temporal attention - run inside
-//     it; everything those need besides the partial sums is loaded BEFORE the rendezvous.
+//     it; everything those need besides the partial sums is loaded BEFORE the partial sums.
 // Warp roles (256 threads): 0 = W producer, 1 = A producer, 2 = TMEM allocator + MMA issue (warp-uniform loop, elect.sync); all 8 warps drain the
 // accumulator (one TMEM lane quadrant each, half of the columns) and reduce.  (An optional L2 prefetch of the next GEMM's
 // weights, issued once the accumulator is complete, is off by default: GemmParams::prefetch, see dit_engine.cu.)
@@ -659,9 +661,19 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         } else {
             if (threadIdx.x == 128) SK_STAMP(5);                                   // this warp's partials issued
             // The other CTAs' partial sums become visible ~0.5 us after they were issued; loads sent before that come back
-            // without them and cost a second round trip.  Wait that long before the first attempt.
+            // without them and cost a second round trip.  Wait that long before the first attempt - and give the TMEM back
+            // meanwhile, off the kernel's exit path: the other warps only signal that they have read their part of the
+            // accumulator (named barrier 1, non-blocking arrive), warp 2 waits for them and deallocates.
+            const long long t0 = clock64();
+            tcgen05_fence_before();
+            if (warp == 2) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                tcgen05_fence_after();
+                tmem_dealloc(tmem_base, tmem_cols);
+            } else {
+                asm volatile("bar.arrive 1, 256;" ::: "memory");
+            }
             if (GTAV_SK_TAG_DELAY > 0) {
-                const long long t0 = clock64();
                 while (clock64() - t0 < GTAV_SK_TAG_DELAY) {}
             }
             if (threadIdx.x == 128) SK_STAMP(6);
@@ -707,7 +719,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         }
         if (threadIdx.x == 128) SK_STAMP(7);
     }
-    if ((S == 1 || tagged) && gemm_cta) {          // no split / tagged: warps read the accumulator until shortly before here
+    if (S == 1 && gemm_cta) {                      // no split: the epilogue warps read the accumulator until here
         tcgen05_fence_before();
         __syncthreads();
         if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
