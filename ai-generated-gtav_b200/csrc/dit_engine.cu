@@ -282,7 +282,7 @@ int run_backbone(gtav_dit_plan_s* p, const Shape* sh, int mode, const void* x, i
 extern "C" {
 
 const char* gtav_last_error(void) { return get_error(); }
-int gtav_abi_version(void) { return 3; }
+int gtav_abi_version(void) { return 4; }
 
 int gtav_dit_create(const gtav_dit_config* cfg, const gtav_dit_weights* w, gtav_dit_t* out) {
     if (!cfg || !w || !out) { set_error("dit_create: null argument"); return -1; }

@@ -32,7 +32,7 @@ extern "C" {
 typedef struct CUstream_st* gtav_stream_t; /* == cudaStream_t */
 
 const char* gtav_last_error(void);
-/* ABI version; bumped on any signature change. */
+/* ABI version; bumped on any signature change or new entry point (4: gtav_gemm_skinny_tagged_bf16, larger DiT plan workspace). */
 int gtav_abi_version(void);
 
 /* ------------------------------------------------------------------------------------------

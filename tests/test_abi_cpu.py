@@ -33,7 +33,7 @@ def test_library_exports_exactly_the_header(native):
     out = subprocess.run(["nm", "-D", "--defined-only", native.LIB_PATH], capture_output=True, text=True).stdout
     exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l)
     assert exported == decl, set(exported) ^ set(decl)          # nothing else leaks out of the .so
-    assert lib.gtav_abi_version() == 3
+    assert lib.gtav_abi_version() == 4
 
 
 def test_library_is_sm100a_tcgen05(native):
