@@ -576,7 +576,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     // ---- past griddepcontrol.wait: the previous kernels' results are visible.  Start the loads the reduce will need.
     // Rendezvous group: the S CTAs of this row block (group rb of `counters`, 4 ints each), or, in the fused modes, ALL
     // CTAs of the grid (group 64).
-    int* const meet = p.counters + 4 * (FUSE == SK_FUSE_NONE ? rb : 64);
+    int* const meet = tagged ? nullptr : p.counters + 4 * (FUSE == SK_FUSE_NONE ? rb : 64);     // (tagged: no counters at all)
     const int meet_n = FUSE == SK_FUSE_NONE ? S : static_cast<int>(gridDim.x);
     int sense0 = 0;
     if (threadIdx.x == 128 && meet_n > 1 && !tagged) sense0 = ld_acquire_gpu(meet + 2);
