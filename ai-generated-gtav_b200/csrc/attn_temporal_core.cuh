@@ -46,16 +46,31 @@ __device__ __forceinline__ uint32_t temporal_last_core(int tc, float2 qx, float2
     // rotate in fp32, round once to bf16 (apply_rotary_emb casts back to the input dtype)
     const float2 q = rotary_pair_rn(qx, cs);
     const float2 kn = rotary_pair_rn(kx, cs);
+    // Scores of all TMAX + 1 key slots at once: the dot products' warp reductions are five dependent shuffles each, and
+    // reduced one key after the other (behind a branch per key) they were a chain of 5 (tc + 1) shuffle latencies in the
+    // fused reduce of every temporal to_qkv launch.  Here each butterfly step issues the shuffles of all slots back to back
+    // (slots beyond tc reduce a copy of the frame's own key and are ignored); per key the additions are warp_sum's, in its
+    // order - same bits.
     float s[TMAX + 1];
+#pragma unroll
+    for (int j = 0; j <= TMAX; ++j) {
+        float2 k = kn;
+        if (j < TMAX && j < tc) k = unpack_bf16x2(kc[j < TMAX ? j : 0]);
+        s[j] = dot_pair_rn(q, k);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j <= TMAX; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+    }
     float m = -INFINITY;
 #pragma unroll
     for (int j = 0; j <= TMAX; ++j) {
-        s[j] = 0.f;
         if (j <= tc) {                                       // key j: cached frame j, or (j == tc) the frame's own
-            float2 k = kn;
-            if (j < TMAX && j < tc) k = unpack_bf16x2(kc[j < TMAX ? j : 0]);
-            s[j] = __fmul_rn(warp_sum(dot_pair_rn(q, k)), 0.125f);
+            s[j] = __fmul_rn(s[j], 0.125f);
             m = fmaxf(m, s[j]);
+        } else {
+            s[j] = 0.f;
         }
     }
     float l = 0.f;
