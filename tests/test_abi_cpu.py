@@ -52,6 +52,11 @@ def test_host_side_argument_checks_need_no_gpu(native):
     h = native.vp()
     rc = lib.gtav_dit_create(C.byref(cfg), C.byref(native.DitWeights()), C.byref(h))
     assert rc != 0 and b"unsupported geometry" in lib.gtav_last_error()
+    # the tagged weight-streaming GEMM refuses a missing workspace and a parity outside {0, 1} before touching the device
+    args = [None, 1024, None, 1024, None, 1024, 144, 1024, 1024, native.EPI_STORE, None, None, 0, None, 0, None, 144, 0]
+    assert lib.gtav_gemm_skinny_tagged_bf16(*args, None, 1, None) != 0 and b"workspace" in lib.gtav_last_error()
+    assert lib.gtav_gemm_skinny_tagged_bf16(*args, 4096, 2, None) != 0 and b"parity" in lib.gtav_last_error()
+    assert lib.gtav_gemm_skinny_workspace_bytes(144) == 160 * 144 * 128 * 4
 
 
 def test_dit_state_dict_contract():
